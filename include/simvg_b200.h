@@ -69,6 +69,36 @@ typedef struct simvgb_gemm_args {
 
 int simvgb_gemm(const simvgb_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused multiway self-attention (flash-style; S, O, dK, dV, dQ accumulators in TMEM).
+ * Replaces torchscale MultiheadAttention.forward's bmm -> masked_fill(key_padding_mask, -inf) ->
+ * softmax(dtype=fp32) -> bmm (called at beit3_base.py:137-145) and its backward.
+ * Vision and text tokens live in separate token-major buffers (multiway experts A / B); per sample the
+ * attended sequence is [Lv vision | Lt text].  q must already be scaled by head_dim^-0.5.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct simvgb_attn_args {
+  int32_t B, H, Lv, Lt, head_dim;   /* head_dim must be 64 */
+  const void* qkv_v;      /* bf16 [B*Lv, 3*H*64]   row = q | k | v                       */
+  const void* qkv_t;      /* bf16 [B*Lt, 3*H*64]                                          */
+  const void* text_pad;   /* uint8 [B, Lt], 1 = padded text token (masked key), or NULL    */
+  void* out_v;            /* bf16 [B*Lv, H*64]   fwd: written; bwd: read                  */
+  void* out_t;            /* bf16 [B*Lt, H*64]                                             */
+  float* lse;             /* fp32 [B, H, simvgb_attn_lse_stride(Lv, Lt)] log2-domain       */
+  /* backward only */
+  const void* dout_v;     /* bf16 [B*Lv, H*64] */
+  const void* dout_t;     /* bf16 [B*Lt, H*64] */
+  void* dqkv_v;           /* bf16 [B*Lv, 3*H*64] out: gradient w.r.t. the *unscaled* q, k, v */
+  void* dqkv_t;           /* bf16 [B*Lt, 3*H*64] */
+  float* delta;           /* fp32 workspace [B, H, lse_stride] */
+  float* dq_acc_v;        /* fp32 workspace [B*Lv, H*64] (zeroed by the call) */
+  float* dq_acc_t;        /* fp32 workspace [B*Lt, H*64] */
+  float q_scale;          /* head_dim^-0.5, applied to dq on the way out */
+} simvgb_attn_args;
+
+int simvgb_attn_lse_stride(int Lv, int Lt);
+int simvgb_attn_fwd(const simvgb_attn_args* args, void* stream);
+int simvgb_attn_bwd(const simvgb_attn_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,152 @@
+"""GPU bring-up check for the fused multiway attention kernels (forward + backward) vs a torch fp32 reference."""
+import ctypes
+import json
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from simvg_b200 import _lib as L  # noqa: E402
+
+
+class AttnArgs(ctypes.Structure):
+    _fields_ = [
+        ("B", L.c_int), ("H", L.c_int), ("Lv", L.c_int), ("Lt", L.c_int), ("head_dim", L.c_int),
+        ("qkv_v", L.c_vp), ("qkv_t", L.c_vp), ("text_pad", L.c_vp),
+        ("out_v", L.c_vp), ("out_t", L.c_vp), ("lse", L.c_vp),
+        ("dout_v", L.c_vp), ("dout_t", L.c_vp), ("dqkv_v", L.c_vp), ("dqkv_t", L.c_vp),
+        ("delta", L.c_vp), ("dq_acc_v", L.c_vp), ("dq_acc_t", L.c_vp), ("q_scale", L.c_f32),
+    ]
+
+
+def run(B, H, Lv, Lt, pad_counts=None, check=True, iters=0, tag=""):
+    dev = torch.device("cuda:0")
+    D = H * 64
+    lib = L.lib()
+    lib.simvgb_attn_lse_stride.restype = L.c_int
+    stride = lib.simvgb_attn_lse_stride(Lv, Lt)
+    torch.manual_seed(1)
+    qkv_v = (torch.randn(B * Lv, 3 * D, device=dev) * 0.7).bfloat16()
+    qkv_t = (torch.randn(B * Lt, 3 * D, device=dev) * 0.7).bfloat16()
+    qkv_v[:, :D] *= 0.125
+    qkv_t[:, :D] *= 0.125
+    pad = torch.zeros(B, Lt, dtype=torch.uint8, device=dev)
+    if pad_counts is not None:
+        for b, n in enumerate(pad_counts):
+            if n > 0:
+                pad[b, Lt - n:] = 1
+    out_v = torch.empty(B * Lv, D, device=dev, dtype=torch.bfloat16)
+    out_t = torch.empty(B * Lt, D, device=dev, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, stride, device=dev)
+    dout_v = (torch.randn(B * Lv, D, device=dev)).bfloat16()
+    dout_t = (torch.randn(B * Lt, D, device=dev)).bfloat16()
+    dqkv_v = torch.zeros(B * Lv, 3 * D, device=dev, dtype=torch.bfloat16)
+    dqkv_t = torch.zeros(B * Lt, 3 * D, device=dev, dtype=torch.bfloat16)
+    delta = torch.zeros(B, H, stride, device=dev)
+    dq_acc_v = torch.empty(B * Lv, D, device=dev)
+    dq_acc_t = torch.empty(B * Lt, D, device=dev)
+    a = AttnArgs()
+    a.B, a.H, a.Lv, a.Lt, a.head_dim = B, H, Lv, Lt, 64
+    a.qkv_v, a.qkv_t, a.text_pad = qkv_v.data_ptr(), qkv_t.data_ptr(), pad.data_ptr()
+    a.out_v, a.out_t, a.lse = out_v.data_ptr(), out_t.data_ptr(), lse.data_ptr()
+    a.dout_v, a.dout_t = dout_v.data_ptr(), dout_t.data_ptr()
+    a.dqkv_v, a.dqkv_t = dqkv_v.data_ptr(), dqkv_t.data_ptr()
+    a.delta, a.dq_acc_v, a.dq_acc_t = delta.data_ptr(), dq_acc_v.data_ptr(), dq_acc_t.data_ptr()
+    a.q_scale = 0.125
+    L.check(lib.simvgb_attn_fwd(ctypes.byref(a), L.stream_ptr()), "attn_fwd")
+    torch.cuda.synchronize()
+    L.check(lib.simvgb_attn_bwd(ctypes.byref(a), L.stream_ptr()), "attn_bwd")
+    torch.cuda.synchronize()
+    res = {}
+    if check:
+        # reference: joint sequence [vision | text] per sample, fp32
+        x = torch.cat([qkv_v.view(B, Lv, 3 * D), qkv_t.view(B, Lt, 3 * D)], 1).float()
+        x.requires_grad_(True)
+        q, k, v = x.split(D, dim=-1)
+        Lx = Lv + Lt
+        q = q.view(B, Lx, H, 64).transpose(1, 2)
+        k = k.view(B, Lx, H, 64).transpose(1, 2)
+        v = v.view(B, Lx, H, 64).transpose(1, 2)
+        s = q @ k.transpose(-1, -2)
+        kpm = torch.cat([torch.zeros(B, Lv, dtype=torch.bool, device=dev), pad.bool()], 1)
+        s = s.masked_fill(kpm[:, None, None, :], float("-inf"))
+        pr = torch.softmax(s, dim=-1)
+        o = (pr @ v).transpose(1, 2).reshape(B, Lx, D)
+        do = torch.cat([dout_v.view(B, Lv, D), dout_t.view(B, Lt, D)], 1).float()
+        o.backward(do)
+        g = x.grad
+        g = torch.cat([g[..., :D] / 0.125 * 0.125, g[..., D:]], -1)  # dq w.r.t. scaled q; kernel applies q_scale
+        # kernel returns gradient wrt *unscaled* q: dq_unscaled = 0.125 * dq_scaled
+        g_q = x.grad[..., :D] * 0.125
+        ref_o_v, ref_o_t = o[:, :Lv].reshape(B * Lv, D), o[:, Lv:].reshape(B * Lt, D)
+
+        def rel(x_, r_):
+            return ((x_.float() - r_).abs().max() / r_.abs().max().clamp_min(1e-20)).item()
+        res["o_v"] = rel(out_v, ref_o_v)
+        res["o_t"] = rel(out_t, ref_o_t)
+        gv, gt = x.grad[:, :Lv].reshape(B * Lv, 3 * D), x.grad[:, Lv:].reshape(B * Lt, 3 * D)
+        res["dq_v"] = rel(dqkv_v[:, :D], gv[:, :D] * 0.125)
+        res["dk_v"] = rel(dqkv_v[:, D:2 * D], gv[:, D:2 * D])
+        res["dv_v"] = rel(dqkv_v[:, 2 * D:], gv[:, 2 * D:])
+        res["dq_t"] = rel(dqkv_t[:, :D], gt[:, :D] * 0.125)
+        res["dk_t"] = rel(dqkv_t[:, D:2 * D], gt[:, D:2 * D])
+        res["dv_t"] = rel(dqkv_t[:, 2 * D:], gt[:, 2 * D:])
+        ok = all(v_ == v_ and v_ < 3e-2 for v_ in res.values())
+        print("%s B=%d H=%d Lv=%d Lt=%d: %s  %s" % (tag, B, H, Lv, Lt, " ".join("%s=%.2e" % kv for kv in res.items()), "OK" if ok else "FAIL"), flush=True)
+        res["ok"] = ok
+    if iters:
+        for fn, name, mult in ((lib.simvgb_attn_fwd, "fwd", 1.0), (lib.simvgb_attn_bwd, "bwd", 2.5)):
+            for _ in range(3):
+                fn(ctypes.byref(a), L.stream_ptr())
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn(ctypes.byref(a), L.stream_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            Lx = Lv + Lt
+            fl = 4.0 * B * H * Lx * Lx * 64 * mult
+            print("time %s B=%d H=%d Lv=%d Lt=%d: %.3f ms  %.0f TFLOP/s (algorithmic)" % (name, B, H, Lv, Lt, ms, fl / ms / 1e9), flush=True)
+            res["ms_" + name] = ms
+            res["tflops_" + name] = fl / ms / 1e9
+    return res
+
+
+def main():
+    L.check(L.lib().simvgb_device_check(0), "device_check")
+    out = {}
+    ok = True
+    cases = [
+        ("tiny", 2, 2, 100, 20, [0, 7]),
+        ("cfg1", 2, 12, 197, 20, [3, 12]),
+        ("p32", 3, 4, 401, 20, [0, 5, 15]),
+        ("exact128", 2, 2, 256, 20, [1, 0]),
+        ("notext", 1, 2, 300, 0, None),
+        ("cfg2s", 2, 12, 1601, 20, [2, 9]),
+        ("l768", 1, 4, 2305, 20, [4]),
+    ]
+    only = sys.argv[1:]
+    for tag, B, H, Lv, Lt, pads in cases:
+        if only and tag not in only:
+            continue
+        if Lt == 0:
+            continue  # text-less path is exercised through the vision-only GEMMs; attention always has text in SimVG
+        r = run(B, H, Lv, Lt, pads, tag=tag)
+        out[tag] = r
+        ok = ok and r.get("ok", False)
+    if ok:
+        out["time_cfg2"] = run(64, 12, 1601, 20, [i % 14 for i in range(64)], check=False, iters=5, tag="time")
+        out["time_p32"] = run(64, 12, 401, 20, [i % 14 for i in range(64)], check=False, iters=5, tag="time")
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/attn_check.json", "w") as f:
+        json.dump({"ok": ok, "results": out}, f, indent=1)
+    print("ALL OK" if ok else "SOME FAILED")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
