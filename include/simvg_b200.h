@@ -99,6 +99,63 @@ int simvgb_attn_lse_stride(int Lv, int Lt);
 int simvgb_attn_fwd(const simvgb_attn_args* args, void* stream);
 int simvgb_attn_bwd(const simvgb_attn_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm (HBM-bound, coalesced 16/32 B per lane).  C must be a multiple of 256.
+ * Replaces the multiway nn.LayerNorm calls self_attn_layer_norm / final_layer_norm / inner_attn_ln /
+ * ffn_layernorm / encoder.layer_norm (beit3_base.py:41,86,136,157,228,396-397; torchscale A.4, A.5) — the
+ * caller launches once per expert (vision rows with the A parameters, text rows with the B parameters).
+ * ------------------------------------------------------------------------------------------------ */
+int simvgb_ln_fwd(const void* x, int x_is_bf16, void* y, int y_is_bf16, const float* gamma, const float* beta,
+                  float* mean, float* rstd, int64_t rows, int C, float eps, void* stream);
+
+/* Backward.  mode 0: residual-stream LN — dres_out = dres_in + LN'(dy), optionally also emits
+ *   dyb = bf16(row_scale * dres_out) (the dY operand of the preceding out_proj / fc2 GEMMs) and
+ *   dbias_prev += colsum(row_scale * dres_out) (their bias gradient).           (beit3_base.py:123-124,146-169)
+ * mode 1: inner attention LN — dx(bf16) = LN'(dy).
+ * mode 2: FFN LN fused with GELU backward — dx(bf16) = LN'(dy) * gelu'(u), dbias_prev += colsum(dx) (fc1 bias). */
+typedef struct simvgb_ln_bwd_args {
+  int32_t mode, C;
+  int64_t rows;
+  const void* x;          /* LN input: fp32 (mode 0) / bf16 (modes 1, 2) */
+  const void* dy;         /* bf16, or fp32 if dy_is_f32 */
+  int32_t dy_is_f32;
+  const float* gamma;
+  const float* mean;
+  const float* rstd;
+  float* dgamma;          /* [C] accumulated (+=) */
+  float* dbeta;           /* [C] accumulated (+=) */
+  const float* dres_in;   /* mode 0; NULL = zero */
+  float* dres_out;        /* mode 0 (may alias dres_in) */
+  void* dyb;              /* mode 0 optional bf16 [rows, C] */
+  const float* row_scale; /* optional per-sample DropPath scale */
+  int32_t rows_per_scale;
+  float* dbias_prev;      /* optional [C] accumulated (+=) */
+  void* dx;               /* modes 1, 2: bf16 [rows, C] */
+  const void* u;          /* mode 2: bf16 pre-activation */
+} simvgb_ln_bwd_args;
+int simvgb_ln_bwd(const simvgb_ln_bwd_args* args, void* stream);
+
+/* out[c] += sum_r s(r) * in[r, c]; optional out_bf16[r, c] = bf16(s(r) * in[r, c]) with s(r) = row_scale[r / rows_per_scale]
+ * (bias gradients: the reduction autograd performs for nn.Linear.bias). */
+int simvgb_colsum(const void* in, int in_is_bf16, float* out, void* out_bf16, const float* row_scale,
+                  int rows_per_scale, int64_t rows, int C, int64_t ld, void* stream);
+int simvgb_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+
+/* Embedding assembly (torchscale VisionEmbedding / TextEmbedding / PositionalEmbedding, A.6-A.7;
+ * Encoder.forward_embedding beit3_base.py:317-334 and the pad-zeroing at :367). */
+int simvgb_im2col_patch(const float* img, void* cols_bf16, int B, int S, int P, void* stream);
+int simvgb_embed_vision(const float* patch, const float* cls, const float* posA, float* xv, int B, int N, int D, void* stream);
+int simvgb_embed_text(const float* table, const int64_t* ids, const void* pad_u8, const float* posB, float* xt, int B,
+                      int Lt, int D, void* stream);
+
+/* Global-norm clip + Adam(amsgrad) on flat fp32 buffers (apis/train.py:81-83; core/optimizer.py:52-68).
+ * grad_sumsq: device scalar holding sum(g^2) over ALL parameters (simvgb_sumsq accumulates into it); the clip
+ * coefficient min(1, max_norm / (sqrt(sumsq) + 1e-6)) is evaluated on the device — no host sync. */
+int simvgb_sumsq(const float* g, int64_t n, float* out, void* stream);
+int simvgb_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, int step, const float* grad_sumsq, float max_norm,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

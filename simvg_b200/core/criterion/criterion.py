@@ -1,0 +1,129 @@
+"""Hungarian-matched set criterion (mirrors /root/reference/simvg/core/criterion/criterion.py:69-271 and detrex's
+HungarianMatcher).
+
+Same interface as the reference (`SetCriterion(num_classes, matcher, weight_dict, eos_coef, loss_class_type)(outputs,
+targets)` with per-sample target dicts), but the REC case SimVG trains on — one query, one ground-truth box per sample —
+is matched without leaving the device: the assignment is the identity, so the reference's 6 `C.cpu()` + scipy round
+trips per step disappear.  Any other case (nq > 1, gREC multi-target) takes the exact scipy path.
+"""
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from simvg_b200.core.box_ops import box_cxcywh_to_xyxy, generalized_box_iou
+from simvg_b200.utils.distributed import get_world_size, is_dist_avail_and_initialized
+
+
+class HungarianMatcher(nn.Module):
+    def __init__(self, cost_class=1.0, cost_bbox=1.0, cost_giou=1.0, cost_class_type="ce_cost", alpha=0.25, gamma=2.0):
+        super().__init__()
+        assert cost_class_type == "ce_cost", "SimVG builds the matcher with ce_cost (tgqs_kd_detr_head.py:132-137)"
+        self.cost_class, self.cost_bbox, self.cost_giou = cost_class, cost_bbox, cost_giou
+
+    @torch.no_grad()
+    def forward(self, outputs, targets):
+        logits, boxes = outputs["pred_logits"], outputs["pred_boxes"]
+        B, nq = logits.shape[:2]
+        sizes = [len(t["boxes"]) for t in targets]
+        if nq == 1 and all(s == 1 for s in sizes):  # identity assignment, no host sync
+            z = torch.zeros(1, dtype=torch.int64, device=logits.device)
+            return [(z, z) for _ in range(B)]
+        from scipy.optimize import linear_sum_assignment
+        prob = logits.flatten(0, 1).softmax(-1)
+        out_bbox = boxes.flatten(0, 1)
+        tgt_ids = torch.cat([t["labels"] for t in targets])
+        tgt_bbox = torch.cat([t["boxes"] for t in targets])
+        C = self.cost_bbox * torch.cdist(out_bbox, tgt_bbox, p=1) + self.cost_class * (-prob[:, tgt_ids]) + \
+            self.cost_giou * (-generalized_box_iou(box_cxcywh_to_xyxy(out_bbox), box_cxcywh_to_xyxy(tgt_bbox)))
+        C = C.view(B, nq, -1).cpu()
+        idx = [linear_sum_assignment(c[i]) for i, c in enumerate(C.split(sizes, -1))]
+        dev = logits.device
+        return [(torch.as_tensor(i, dtype=torch.int64, device=dev), torch.as_tensor(j, dtype=torch.int64, device=dev))
+                for i, j in idx]
+
+
+def sigmoid_focal_loss(inputs, targets, num_boxes, alpha=0.25, gamma=2.0):
+    prob = inputs.sigmoid()
+    ce = F.binary_cross_entropy_with_logits(inputs, targets, reduction="none")
+    p_t = prob * targets + (1 - prob) * (1 - targets)
+    loss = ce * ((1 - p_t) ** gamma)
+    if alpha >= 0:
+        loss = (alpha * targets + (1 - alpha) * (1 - targets)) * loss
+    return loss.mean(1).sum() / num_boxes
+
+
+class SetCriterion(nn.Module):
+    def __init__(self, num_classes, matcher, weight_dict, losses: List[str] = ("class", "boxes"), eos_coef=0.1,
+                 loss_class_type="focal_loss", alpha=0.25, gamma=2.0):
+        super().__init__()
+        assert loss_class_type in ["ce_loss", "focal_loss", "weighted_ce_loss"], \
+            "only support ce loss and focal loss for computing classification loss"
+        self.num_classes, self.matcher, self.weight_dict, self.losses = num_classes, matcher, weight_dict, list(losses)
+        self.alpha, self.gamma, self.eos_coef, self.loss_class_type = alpha, gamma, eos_coef, loss_class_type
+        if loss_class_type in ["ce_loss", "weighted_ce_loss"]:
+            w = torch.ones(num_classes + 1)
+            w[-1] = eos_coef
+            self.register_buffer("empty_weight", w)
+
+    @staticmethod
+    def _src_idx(indices):
+        return (torch.cat([torch.full_like(s, i) for i, (s, _) in enumerate(indices)]), torch.cat([s for s, _ in indices]))
+
+    def loss_labels(self, outputs, targets, indices, num_boxes):
+        logits = outputs["pred_logits"]
+        idx = self._src_idx(indices)
+        tcls_o = torch.cat([t["labels"][j] for t, (_, j) in zip(targets, indices)])
+        tcls = torch.full(logits.shape[:2], self.num_classes, dtype=torch.int64, device=logits.device)
+        tcls[idx] = tcls_o
+        if self.loss_class_type == "ce_loss":
+            loss = F.cross_entropy(logits.transpose(1, 2), tcls, self.empty_weight)
+        elif self.loss_class_type == "weighted_ce_loss":   # criterion.py:128-137
+            wq = torch.full(logits.shape[:2], 0.1, device=logits.device)
+            wq[idx] = 1.0
+            loss = F.cross_entropy(logits.transpose(1, 2), tcls, self.empty_weight, reduction="none")
+            loss = (wq * loss).mean(-1).sum()
+        else:
+            onehot = torch.zeros(logits.shape[0], logits.shape[1], logits.shape[2] + 1, dtype=logits.dtype, device=logits.device)
+            onehot.scatter_(2, tcls.unsqueeze(-1), 1)
+            loss = sigmoid_focal_loss(logits, onehot[:, :, :-1], num_boxes, self.alpha, self.gamma) * logits.shape[1]
+        return {"loss_class": loss}
+
+    def loss_boxes(self, outputs, targets, indices, num_boxes):
+        idx = self._src_idx(indices)
+        src = outputs["pred_boxes"][idx]
+        tgt = torch.cat([t["boxes"][j] for t, (_, j) in zip(targets, indices)], dim=0)
+        l1 = F.l1_loss(src, tgt, reduction="none")
+        giou = 1 - torch.diag(generalized_box_iou(box_cxcywh_to_xyxy(src), box_cxcywh_to_xyxy(tgt)))
+        if self.loss_class_type == "weighted_ce_loss":     # criterion.py:175-182,193-200
+            tw = torch.cat([t["weight"][j] if len(t["weight"][j]) else torch.zeros(1, device=src.device)
+                            for t, (_, j) in zip(targets, indices)]).squeeze()
+            l1 = l1.sum(-1) * tw
+            giou = giou * tw
+        return {"loss_bbox": l1.sum() / num_boxes, "loss_giou": giou.sum() / num_boxes}
+
+    def get_loss(self, loss, outputs, targets, indices, num_boxes):
+        return {"class": self.loss_labels, "boxes": self.loss_boxes}[loss](outputs, targets, indices, num_boxes)
+
+    def forward(self, outputs, targets, return_indices=False):
+        main = {k: v for k, v in outputs.items() if k != "aux_outputs"}
+        indices = self.matcher(main, targets)
+        num_boxes = float(sum(len(t["labels"]) for t in targets))   # host-side count: no .item() sync
+        if is_dist_avail_and_initialized():
+            nb = torch.as_tensor([num_boxes], dtype=torch.float, device=outputs["pred_logits"].device)
+            torch.distributed.all_reduce(nb)
+            num_boxes = nb.item()
+        num_boxes = max(num_boxes / get_world_size(), 1.0)
+        losses = {}
+        for name in self.losses:
+            losses.update(self.get_loss(name, outputs, targets, indices, num_boxes))
+        all_idx = [indices]
+        for i, aux in enumerate(outputs.get("aux_outputs", [])):
+            ind = self.matcher(aux, targets)
+            all_idx.insert(-1, ind)
+            for name in self.losses:
+                losses.update({k + "_%d" % i: v for k, v in self.get_loss(name, aux, targets, ind, num_boxes).items()})
+        if return_indices:
+            return losses, all_idx
+        return losses

@@ -1,0 +1,409 @@
+// HBM-bound row kernels of the encoder: LayerNorm forward / backward (with the residual-stream, GELU and bias-gradient
+// work fused in), column sums, dtype casts, embedding assembly.  All of them are coalesced 16/32-byte-per-lane
+// streaming kernels: each lane owns 8 consecutive columns, a row is covered by C/256 warps.
+//
+// Replaces (reference = eager ATen ops): the multiway LayerNorms self_attn_layer_norm / final_layer_norm / inner_attn_ln /
+// ffn_layernorm / encoder.layer_norm (/root/reference/simvg/models/vis_encs/beit/beit3_base.py:41,86,228 and torchscale
+// A.4/A.5), the residual adds (:123-124,151,169), gelu backward, and Encoder.forward_embedding (:317-334).
+#include "common.cuh"
+#include "simvg_b200.h"
+
+namespace simvgb {
+
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                            pack_bf16x2(v[6], v[7]));
+}
+
+// Sum of `val` over the W warps covering one row.  red: smem [rows_per_block][W][2 slots].
+template <int N>
+__device__ __forceinline__ void row_reduce(float (&val)[N], float* red, int rg, int ww, int W, int lane) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) val[i] = warp_sum(val[i]);
+  if (W == 1) return;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) red[(rg * W + ww) * N + i] = val[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float s = 0.f;
+    for (int w = 0; w < W; ++w) s += red[(rg * W + w) * N + i];
+    val[i] = s;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm forward
+template <typename TIn, typename TOut>
+__global__ void ln_fwd_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ rstd,
+                              long long R, int C, int W, int rpb, float eps) {
+  extern __shared__ float red[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rg = warp / W, ww = warp % W;
+  const int col = (ww * 32 + lane) * 8;
+  float g[8], bt[8];
+  load8(gamma + col, g);
+  load8(beta + col, bt);
+  const long long niter = (R + (long long)gridDim.x * rpb - 1) / ((long long)gridDim.x * rpb);
+  for (long long it = 0; it < niter; ++it) {
+    const long long row = (it * gridDim.x + blockIdx.x) * rpb + rg;
+    const bool ok = row < R;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (ok) load8(x + row * C + col, v);
+    float s[1] = {v[0] + v[1] + v[2] + v[3] + v[4] + v[5] + v[6] + v[7]};
+    row_reduce<1>(s, red, rg, ww, W, lane);
+    const float mu = s[0] / C;
+    float q[1] = {0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mu; q[0] += d * d; }
+    row_reduce<1>(q, red, rg, ww, W, lane);
+    const float rs = rsqrtf(q[0] / C + eps);
+    if (ok) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (v[i] - mu) * rs * g[i] + bt[i];
+      store8(y + row * C + col, o);
+      if (ww == 0 && lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm backward
+// mode 0 (residual-stream LN): dres_out = dres_in + LN'(dy);  optional dyb = bf16(row_scale * dres_out) and
+//                              dbias_prev += colsum(row_scale * dres_out)  (out_proj / fc2 bias gradient of the sub-layer
+//                              whose output joined the stream at this point)
+// mode 1 (inner attention LN): dx (bf16) = LN'(dy)
+// mode 2 (FFN LN + GELU):      du (bf16) = LN'(dy) * gelu'(u);  dbias_prev += colsum(du)  (fc1 bias gradient)
+struct LnBwdParams {
+  const void* x;         // LN input: fp32 (mode 0) / bf16 (modes 1,2)
+  const void* dy;        // bf16, or fp32 when dy_f32
+  int dy_f32;
+  const float* gamma;
+  const float* mean;
+  const float* rstd;
+  float* dgamma;
+  float* dbeta;
+  const float* dres_in;  // mode 0, may be null (treated as zero)
+  float* dres_out;       // mode 0
+  bf16* dyb;             // mode 0 optional
+  const float* row_scale;
+  int rows_per_scale;
+  float* dbias_prev;     // optional (modes 0, 2)
+  bf16* dx;              // modes 1, 2
+  const bf16* u;         // mode 2
+  long long R;
+  int C, W, rpb, mode;
+};
+
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__global__ void ln_bwd_kernel(const LnBwdParams p) {
+  extern __shared__ float red[];
+  const int W = p.W, C = p.C, rpb = p.rpb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rg = warp / W, ww = warp % W;
+  const int col = (ww * 32 + lane) * 8;
+  float g[8];
+  load8(p.gamma + col, g);
+  float acc_g[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc_b[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc_p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long niter = (p.R + (long long)gridDim.x * rpb - 1) / ((long long)gridDim.x * rpb);
+  for (long long it = 0; it < niter; ++it) {
+    const long long row = (it * gridDim.x + blockIdx.x) * rpb + rg;
+    const bool ok = row < p.R;
+    float xv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float mu = 0.f, rs = 0.f;
+    if (ok) {
+      if (p.mode == 0) load8(reinterpret_cast<const float*>(p.x) + row * C + col, xv);
+      else load8(reinterpret_cast<const bf16*>(p.x) + row * C + col, xv);
+      if (p.dy_f32) load8(reinterpret_cast<const float*>(p.dy) + row * C + col, dy);
+      else load8(reinterpret_cast<const bf16*>(p.dy) + row * C + col, dy);
+      mu = __ldg(p.mean + row);
+      rs = __ldg(p.rstd + row);
+    }
+    float xh[8], dyg[8];
+    float s[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xh[i] = (xv[i] - mu) * rs;
+      dyg[i] = dy[i] * g[i];
+      s[0] += dyg[i];
+      s[1] += dyg[i] * xh[i];
+      acc_g[i] += dy[i] * xh[i];
+      acc_b[i] += dy[i];
+    }
+    row_reduce<2>(s, red, rg, ww, W, lane);
+    const float c1 = s[0] / C, c2 = s[1] / C;
+    if (ok) {
+      float dx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dx[i] = rs * (dyg[i] - c1 - xh[i] * c2);
+      if (p.mode == 0) {
+        float dr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (p.dres_in != nullptr) load8(p.dres_in + row * C + col, dr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dr[i] += dx[i];
+        store8(p.dres_out + row * C + col, dr);
+        if (p.dyb != nullptr || p.dbias_prev != nullptr) {
+          const float sc = p.row_scale != nullptr ? __ldg(p.row_scale + row / p.rows_per_scale) : 1.0f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { dr[i] *= sc; acc_p[i] += dr[i]; }
+          if (p.dyb != nullptr) store8(p.dyb + row * C + col, dr);
+        }
+      } else if (p.mode == 1) {
+        store8(p.dx + row * C + col, dx);
+      } else {
+        float uv[8];
+        load8(p.u + row * C + col, uv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dx[i] *= gelu_grad(uv[i]); acc_p[i] += dx[i]; }
+        store8(p.dx + row * C + col, dx);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(p.dgamma + col + i, acc_g[i]);
+    atomicAdd(p.dbeta + col + i, acc_b[i]);
+    if (p.dbias_prev != nullptr) atomicAdd(p.dbias_prev + col + i, acc_p[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ column sum / scaled cast
+// out[c] += sum_r scale(r) * in[r, c];  optional ob = bf16(scale(r) * in[r, c])   (in: bf16 or fp32)
+template <typename TIn>
+__global__ void colsum_kernel(const TIn* __restrict__ in, float* __restrict__ out, bf16* __restrict__ ob,
+                              const float* __restrict__ row_scale, int rows_per_scale, long long R, int C, int ld) {
+  // block = 256 threads: 32 column-chunks (8 cols each) x 8 row lanes
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cx) * 8;
+  if (col >= C) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long row = (long long)blockIdx.y * 8 + ry; row < R; row += (long long)gridDim.y * 8) {
+    float v[8];
+    load8(in + row * ld + col, v);
+    const float sc = row_scale != nullptr ? __ldg(row_scale + row / rows_per_scale) : 1.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] *= sc; acc[i] += v[i]; }
+    if (ob != nullptr) store8(ob + row * C + col, v);
+  }
+  if (out != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(out + col + i, acc[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ casts
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float v[8];
+  load8(in + i * 8, v);
+  store8(out + i * 8, v);
+}
+
+// ------------------------------------------------------------------------------------------------ embedding assembly
+// x_v[b, 0] = cls + posA[2];  x_v[b, 1+n] = patch[b*N+n] + posA[3+n]      (VisionEmbedding + PositionalEmbedding, A.6/A.7)
+__global__ void assemble_vision_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+                                       const float* __restrict__ posA, float* __restrict__ xv, int B, int N, int D) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 elements
+  const int d4 = D / 4;
+  const long long total = (long long)B * (N + 1) * d4;
+  if (idx >= total) return;
+  const int c = (idx % d4) * 4;
+  const long long tok = idx / d4;
+  const int l = tok % (N + 1);
+  const long long b = tok / (N + 1);
+  const float4 pos = __ldg(reinterpret_cast<const float4*>(posA + (long long)(2 + l) * D + c));
+  float4 t;
+  if (l == 0) t = __ldg(reinterpret_cast<const float4*>(cls + c));
+  else t = __ldg(reinterpret_cast<const float4*>(patch + (b * N + (l - 1)) * D + c));
+  *reinterpret_cast<float4*>(xv + tok * D + c) = make_float4(t.x + pos.x, t.y + pos.y, t.z + pos.z, t.w + pos.w);
+}
+
+// x_t[b, i] = (text_embed[ids[b,i]] + posB[2+i]) * (1 - pad[b,i])         (beit3_base.py:325-330,367)
+__global__ void assemble_text_kernel(const float* __restrict__ table, const long long* __restrict__ ids,
+                                     const unsigned char* __restrict__ pad, const float* __restrict__ posB,
+                                     float* __restrict__ xt, int B, int Lt, int D) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int d4 = D / 4;
+  const long long total = (long long)B * Lt * d4;
+  if (idx >= total) return;
+  const int c = (idx % d4) * 4;
+  const long long tok = idx / d4;
+  const int i = tok % Lt;
+  const float keep = (pad != nullptr && pad[tok]) ? 0.f : 1.f;
+  const float4 e = __ldg(reinterpret_cast<const float4*>(table + ids[tok] * D + c));
+  const float4 pos = __ldg(reinterpret_cast<const float4*>(posB + (long long)(2 + i) * D + c));
+  *reinterpret_cast<float4*>(xt + tok * D + c) =
+      make_float4((e.x + pos.x) * keep, (e.y + pos.y) * keep, (e.z + pos.z) * keep, (e.w + pos.w) * keep);
+}
+
+// im2col for the stride-P patch conv: img [B,3,S,S] fp32 -> cols [B*N, 3*P*P] bf16 (channel-major, then ky, kx:
+// the flattening order of Conv2d weight [D,3,P,P]).
+__global__ void im2col_patch_kernel(const float* __restrict__ img, bf16* __restrict__ cols, int B, int S, int P) {
+  const int G = S / P;
+  const long long K = 3LL * P * P;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 8 consecutive kx
+  const long long total = (long long)B * G * G * K / 8;
+  if (idx >= total) return;
+  const long long e = idx * 8;
+  const long long row = e / K;
+  const int k = e % K;
+  const int ch = k / (P * P), ky = (k / P) % P, kx = k % P;
+  const int n = row % (G * G);
+  const long long b = row / (G * G);
+  const int gy = n / G, gx = n % G;
+  const float* src = img + ((b * 3 + ch) * S + (gy * P + ky)) * (long long)S + gx * P + kx;
+  float v[8];
+  load8(src, v);
+  store8(cols + e, v);
+}
+
+static int ln_geometry(int C, int* W, int* rpb) {
+  if (C % 256 != 0 || C > 8192) return -1;
+  *W = C / 256;
+  int r = 8 / *W;
+  if (r < 1) r = 1;
+  *rpb = r;
+  return 0;
+}
+
+static int ln_grid(long long R, int rpb) {
+  long long want = (R + rpb - 1) / rpb;
+  long long cap = (long long)sm_count() * 4;
+  return (int)(want < cap ? want : cap);
+}
+
+}  // namespace simvgb
+
+using namespace simvgb;
+
+extern "C" int simvgb_ln_fwd(const void* x, int x_is_bf16, void* y, int y_is_bf16, const float* gamma, const float* beta,
+                             float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
+  int W, rpb;
+  SIMVGB_CHECK(ln_geometry(C, &W, &rpb) == 0, "simvgb_ln_fwd: C=%d must be a multiple of 256 and <= 8192", C);
+  SIMVGB_CHECK(x && y && gamma && beta && mean && rstd, "simvgb_ln_fwd: null pointer");
+  if (rows <= 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int threads = 32 * W * rpb, grid = ln_grid(rows, rpb);
+  const size_t sm = sizeof(float) * rpb * W * 2;
+  if (!x_is_bf16 && y_is_bf16)
+    ln_fwd_kernel<float, bf16><<<grid, threads, sm, s>>>((const float*)x, (bf16*)y, gamma, beta, mean, rstd, rows, C, W, rpb, eps);
+  else if (x_is_bf16 && y_is_bf16)
+    ln_fwd_kernel<bf16, bf16><<<grid, threads, sm, s>>>((const bf16*)x, (bf16*)y, gamma, beta, mean, rstd, rows, C, W, rpb, eps);
+  else if (!x_is_bf16 && !y_is_bf16)
+    ln_fwd_kernel<float, float><<<grid, threads, sm, s>>>((const float*)x, (float*)y, gamma, beta, mean, rstd, rows, C, W, rpb, eps);
+  else
+    ln_fwd_kernel<bf16, float><<<grid, threads, sm, s>>>((const bf16*)x, (float*)y, gamma, beta, mean, rstd, rows, C, W, rpb, eps);
+  SIMVGB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int simvgb_ln_bwd(const simvgb_ln_bwd_args* a, void* stream) {
+  SIMVGB_CHECK(a != nullptr, "simvgb_ln_bwd: null args");
+  int W, rpb;
+  SIMVGB_CHECK(ln_geometry(a->C, &W, &rpb) == 0, "simvgb_ln_bwd: C=%d must be a multiple of 256 and <= 8192", a->C);
+  SIMVGB_CHECK(a->mode >= 0 && a->mode <= 2, "simvgb_ln_bwd: bad mode %d", a->mode);
+  SIMVGB_CHECK(a->x && a->dy && a->gamma && a->mean && a->rstd && a->dgamma && a->dbeta, "simvgb_ln_bwd: null pointer");
+  SIMVGB_CHECK(a->mode != 0 || a->dres_out, "simvgb_ln_bwd: mode 0 needs dres_out");
+  SIMVGB_CHECK(a->mode == 0 || a->dx, "simvgb_ln_bwd: modes 1/2 need dx");
+  SIMVGB_CHECK(a->mode != 2 || a->u, "simvgb_ln_bwd: mode 2 needs u");
+  if (a->rows <= 0) return 0;
+  LnBwdParams p;
+  p.x = a->x; p.dy = a->dy; p.dy_f32 = a->dy_is_f32; p.gamma = a->gamma; p.mean = a->mean; p.rstd = a->rstd;
+  p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dres_in = a->dres_in; p.dres_out = a->dres_out;
+  p.dyb = reinterpret_cast<bf16*>(a->dyb); p.row_scale = a->row_scale;
+  p.rows_per_scale = a->rows_per_scale > 0 ? a->rows_per_scale : 1;
+  p.dbias_prev = a->dbias_prev; p.dx = reinterpret_cast<bf16*>(a->dx); p.u = reinterpret_cast<const bf16*>(a->u);
+  p.R = a->rows; p.C = a->C; p.W = W; p.rpb = rpb; p.mode = a->mode;
+  const int threads = 32 * W * rpb;
+  int grid = ln_grid(a->rows, rpb);
+  ln_bwd_kernel<<<grid, threads, sizeof(float) * rpb * W * 2, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  SIMVGB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int simvgb_colsum(const void* in, int in_is_bf16, float* out, void* out_bf16, const float* row_scale,
+                             int rows_per_scale, int64_t rows, int C, int64_t ld, void* stream) {
+  SIMVGB_CHECK(in && (out || out_bf16), "simvgb_colsum: null pointer");
+  SIMVGB_CHECK(C % 8 == 0 && ld % 8 == 0, "simvgb_colsum: C and ld must be multiples of 8");
+  if (rows <= 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((C / 8 + 31) / 32, 1);
+  long long gy = (rows + 7) / 8;
+  const long long cap = (long long)sm_count() * 8 / grid.x + 1;
+  grid.y = (unsigned)(gy < cap ? gy : cap);
+  const int rps = rows_per_scale > 0 ? rows_per_scale : 1;
+  if (in_is_bf16)
+    colsum_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, out, (bf16*)out_bf16, row_scale, rps, rows, C, (int)ld);
+  else
+    colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)in, out, (bf16*)out_bf16, row_scale, rps, rows, C, (int)ld);
+  SIMVGB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int simvgb_cast_bf16(const float* in, void* out, int64_t n, void* stream) {
+  SIMVGB_CHECK(in && out, "simvgb_cast_bf16: null pointer");
+  SIMVGB_CHECK(n % 8 == 0, "simvgb_cast_bf16: n must be a multiple of 8 (got %lld)", (long long)n);
+  if (n == 0) return 0;
+  const long long n8 = n / 8;
+  cast_f32_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, (bf16*)out, n8);
+  SIMVGB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int simvgb_embed_vision(const float* patch, const float* cls, const float* posA, float* xv, int B, int N, int D,
+                                   void* stream) {
+  SIMVGB_CHECK(patch && cls && posA && xv, "simvgb_embed_vision: null pointer");
+  SIMVGB_CHECK(D % 4 == 0, "simvgb_embed_vision: D must be a multiple of 4");
+  const long long total = (long long)B * (N + 1) * (D / 4);
+  assemble_vision_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(patch, cls, posA, xv, B, N, D);
+  SIMVGB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int simvgb_embed_text(const float* table, const int64_t* ids, const void* pad, const float* posB, float* xt,
+                                 int B, int Lt, int D, void* stream) {
+  SIMVGB_CHECK(table && ids && posB && xt, "simvgb_embed_text: null pointer");
+  SIMVGB_CHECK(D % 4 == 0, "simvgb_embed_text: D must be a multiple of 4");
+  const long long total = (long long)B * Lt * (D / 4);
+  if (total == 0) return 0;
+  assemble_text_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      table, reinterpret_cast<const long long*>(ids), reinterpret_cast<const unsigned char*>(pad), posB, xt, B, Lt, D);
+  SIMVGB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int simvgb_im2col_patch(const float* img, void* cols, int B, int S, int P, void* stream) {
+  SIMVGB_CHECK(img && cols, "simvgb_im2col_patch: null pointer");
+  SIMVGB_CHECK(P % 8 == 0 && S % P == 0, "simvgb_im2col_patch: need P %% 8 == 0 and S %% P == 0 (S=%d P=%d)", S, P);
+  const long long total = (long long)B * (S / P) * (S / P) * 3 * P * P / 8;
+  im2col_patch_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(img, (bf16*)cols, B, S, P);
+  SIMVGB_CUDA(cudaGetLastError());
+  return 0;
+}

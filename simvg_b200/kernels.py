@@ -1,0 +1,270 @@
+"""Tensor-level wrappers over the C ABI of libsimvg_b200.so (include/simvg_b200.h).
+
+PyTorch only owns memory and streams here; every function below launches hand-written sm_100a kernels on the
+current stream and raises if the library or a CUDA device is missing (no CPU / eager fallback).
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+from ._lib import EPI_ATOMIC, EPI_BF16, EPI_F32, EPI_GELU, EPI_RESID  # noqa: F401
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+# Launch counter: number of libsimvg_b200 kernel launches since the last reset (bench.py reports it).
+_launches = [0]
+
+
+def launch_count():
+    return _launches[0]
+
+
+def reset_launch_count():
+    _launches[0] = 0
+
+
+class AttnArgs(ctypes.Structure):
+    _fields_ = [
+        ("B", L.c_int), ("H", L.c_int), ("Lv", L.c_int), ("Lt", L.c_int), ("head_dim", L.c_int),
+        ("qkv_v", L.c_vp), ("qkv_t", L.c_vp), ("text_pad", L.c_vp),
+        ("out_v", L.c_vp), ("out_t", L.c_vp), ("lse", L.c_vp),
+        ("dout_v", L.c_vp), ("dout_t", L.c_vp), ("dqkv_v", L.c_vp), ("dqkv_t", L.c_vp),
+        ("delta", L.c_vp), ("dq_acc_v", L.c_vp), ("dq_acc_t", L.c_vp), ("q_scale", L.c_f32),
+    ]
+
+
+class LnBwdArgs(ctypes.Structure):
+    _fields_ = [
+        ("mode", L.c_int), ("C", L.c_int), ("rows", L.c_i64),
+        ("x", L.c_vp), ("dy", L.c_vp), ("dy_is_f32", L.c_int),
+        ("gamma", L.c_vp), ("mean", L.c_vp), ("rstd", L.c_vp),
+        ("dgamma", L.c_vp), ("dbeta", L.c_vp),
+        ("dres_in", L.c_vp), ("dres_out", L.c_vp), ("dyb", L.c_vp),
+        ("row_scale", L.c_vp), ("rows_per_scale", L.c_int),
+        ("dbias_prev", L.c_vp), ("dx", L.c_vp), ("u", L.c_vp),
+    ]
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _lib_setup():
+    lib = L.lib()
+    if not getattr(lib, "_simvgb_typed", False):
+        lib.simvgb_attn_lse_stride.restype = L.c_int
+        lib.simvgb_ln_fwd.argtypes = [L.c_vp, L.c_int, L.c_vp, L.c_int, L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_i64, L.c_int,
+                                      L.c_f32, L.c_vp]
+        lib.simvgb_colsum.argtypes = [L.c_vp, L.c_int, L.c_vp, L.c_vp, L.c_vp, L.c_int, L.c_i64, L.c_int, L.c_i64, L.c_vp]
+        lib.simvgb_cast_bf16.argtypes = [L.c_vp, L.c_vp, L.c_i64, L.c_vp]
+        lib.simvgb_im2col_patch.argtypes = [L.c_vp, L.c_vp, L.c_int, L.c_int, L.c_int, L.c_vp]
+        lib.simvgb_embed_vision.argtypes = [L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_int, L.c_int, L.c_int, L.c_vp]
+        lib.simvgb_embed_text.argtypes = [L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_int, L.c_int, L.c_int, L.c_vp]
+        lib.simvgb_sumsq.argtypes = [L.c_vp, L.c_i64, L.c_vp, L.c_vp]
+        lib.simvgb_adam_amsgrad.argtypes = [L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_i64, L.c_f32, L.c_f32, L.c_f32,
+                                            L.c_f32, L.c_f32, L.c_int, L.c_vp, L.c_f32, L.c_vp]
+        lib._simvgb_typed = True
+    return lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, bias=None, out=None, out2=None, res=None,
+         scale=1.0, scale_cols=0, row_scale=None, rows_per_scale=1, k_splits=1, accumulate=False, ldo=None):
+    """C[M,N] = epilogue(A(M,K) @ B(N,K)^T).  A: [M,K] (or [K,M] if a_mn), B: [N,K] (or [K,N] if b_mn), bf16.
+
+    Returns `out` (allocated when None: bf16 for the BF16/GELU epilogues, fp32 otherwise)."""
+    L.require_device(A)
+    lib = _lib_setup()
+    a = L.GemmArgs()
+    a.M, a.N, a.K = M, N, K
+    a.a_mn_major, a.b_mn_major = int(a_mn), int(b_mn)
+    a.lda, a.ldb = A.stride(0), B.stride(0)
+    a.A, a.B = A.data_ptr(), B.data_ptr()
+    a.epilogue, a.k_splits = epilogue, k_splits
+    a.bias = _p(bias)
+    if out is None:
+        if epilogue in (EPI_BF16, EPI_GELU):
+            out = torch.empty(M, N, device=A.device, dtype=bf16)
+        elif epilogue == EPI_ATOMIC:
+            out = torch.zeros(M, N, device=A.device, dtype=f32)
+        else:
+            out = torch.empty(M, N, device=A.device, dtype=f32)
+    if epilogue in (EPI_BF16, EPI_GELU):
+        a.out_bf16 = out.data_ptr()
+        if epilogue == EPI_GELU:
+            a.out2_bf16 = out2.data_ptr()
+    else:
+        a.out_f32 = out.data_ptr()
+    a.res_f32 = _p(res)
+    a.ldo = ldo if ldo is not None else out.stride(0)
+    a.scale, a.scale_cols = scale, scale_cols
+    a.row_scale = _p(row_scale)
+    a.rows_per_scale = rows_per_scale
+    a.accumulate = int(accumulate)
+    L.check(lib.simvgb_gemm(ctypes.byref(a), L.c_vp(_stream())), "gemm")
+    _launches[0] += 1
+    return out
+
+
+def wgrad_splits(M, N, K):
+    """Split-K factor for a weight-gradient GEMM (few output tiles, very long K)."""
+    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
+    kb = (K + 63) // 64
+    ks = max(1, min((2 * 148 + tiles - 1) // tiles, kb // 4 if kb >= 8 else 1))
+    return ks
+
+
+def wgrad(dY, X, Dout, Din, R, out=None):
+    """dW[Dout, Din] (+)= dY[R, Dout]^T @ X[R, Din]; both operands read MN-major, fp32 atomics over split-K."""
+    if out is None:
+        out = torch.zeros(Dout, Din, device=dY.device, dtype=f32)
+    return gemm(dY, X, Dout, Din, R, a_mn=True, b_mn=True, epilogue=EPI_ATOMIC, out=out,
+                k_splits=wgrad_splits(Dout, Din, R))
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def attn_lse_stride(Lv, Lt):
+    return _lib_setup().simvgb_attn_lse_stride(Lv, Lt)
+
+
+def _attn_args(B, H, Lv, Lt, qkv_v, qkv_t, pad, out_v, out_t, lse):
+    a = AttnArgs()
+    a.B, a.H, a.Lv, a.Lt, a.head_dim = B, H, Lv, Lt, 64
+    a.qkv_v, a.qkv_t, a.text_pad = _p(qkv_v), _p(qkv_t), _p(pad)
+    a.out_v, a.out_t, a.lse = _p(out_v), _p(out_t), _p(lse)
+    a.q_scale = 0.125
+    return a
+
+
+def attn_fwd(qkv_v, qkv_t, pad, B, H, Lv, Lt):
+    L.require_device(qkv_v)
+    lib = _lib_setup()
+    D = H * 64
+    dev = qkv_v.device
+    out_v = torch.empty(B * Lv, D, device=dev, dtype=bf16)
+    out_t = torch.empty(B * Lt, D, device=dev, dtype=bf16)
+    lse = torch.empty(B, H, attn_lse_stride(Lv, Lt), device=dev, dtype=f32)
+    a = _attn_args(B, H, Lv, Lt, qkv_v, qkv_t, pad, out_v, out_t, lse)
+    L.check(lib.simvgb_attn_fwd(ctypes.byref(a), L.c_vp(_stream())), "attn_fwd")
+    _launches[0] += 1
+    return out_v, out_t, lse
+
+
+def attn_bwd(qkv_v, qkv_t, pad, out_v, out_t, lse, dout_v, dout_t, B, H, Lv, Lt, ws=None):
+    lib = _lib_setup()
+    D = H * 64
+    dev = qkv_v.device
+    dqkv_v = torch.empty(B * Lv, 3 * D, device=dev, dtype=bf16)
+    dqkv_t = torch.empty(B * Lt, 3 * D, device=dev, dtype=bf16)
+    if ws is None:
+        ws = {}
+    key = (B, H, Lv, Lt)
+    if ws.get("key") != key:
+        ws["key"] = key
+        ws["delta"] = torch.empty(B, H, attn_lse_stride(Lv, Lt), device=dev, dtype=f32)
+        ws["dq_v"] = torch.empty(B * Lv, D, device=dev, dtype=f32)
+        ws["dq_t"] = torch.empty(B * Lt, D, device=dev, dtype=f32)
+    a = _attn_args(B, H, Lv, Lt, qkv_v, qkv_t, pad, out_v, out_t, lse)
+    a.dout_v, a.dout_t = _p(dout_v), _p(dout_t)
+    a.dqkv_v, a.dqkv_t = _p(dqkv_v), _p(dqkv_t)
+    a.delta, a.dq_acc_v, a.dq_acc_t = _p(ws["delta"]), _p(ws["dq_v"]), _p(ws["dq_t"])
+    L.check(lib.simvgb_attn_bwd(ctypes.byref(a), L.c_vp(_stream())), "attn_bwd")
+    _launches[0] += 5
+    return dqkv_v, dqkv_t
+
+
+# ---------------------------------------------------------------------------------------------- row kernels
+def ln_fwd(x, gamma, beta, eps, out_dtype=bf16):
+    L.require_device(x)
+    lib = _lib_setup()
+    R, C = x.shape
+    y = torch.empty(R, C, device=x.device, dtype=out_dtype)
+    mean = torch.empty(R, device=x.device, dtype=f32)
+    rstd = torch.empty(R, device=x.device, dtype=f32)
+    L.check(lib.simvgb_ln_fwd(x.data_ptr(), int(x.dtype == bf16), y.data_ptr(), int(out_dtype == bf16), gamma.data_ptr(),
+                              beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), R, C, eps, _stream()), "ln_fwd")
+    _launches[0] += 1
+    return y, mean, rstd
+
+
+def ln_bwd(mode, x, dy, gamma, mean, rstd, dgamma, dbeta, *, dres_in=None, dres_out=None, dyb=None, row_scale=None,
+           rows_per_scale=1, dbias_prev=None, dx=None, u=None):
+    lib = _lib_setup()
+    R, C = x.shape
+    a = LnBwdArgs()
+    a.mode, a.C, a.rows = mode, C, R
+    a.x, a.dy, a.dy_is_f32 = x.data_ptr(), dy.data_ptr(), int(dy.dtype == f32)
+    a.gamma, a.mean, a.rstd = gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    a.dgamma, a.dbeta = dgamma.data_ptr(), dbeta.data_ptr()
+    a.dres_in, a.dres_out, a.dyb = _p(dres_in), _p(dres_out), _p(dyb)
+    a.row_scale, a.rows_per_scale = _p(row_scale), rows_per_scale
+    a.dbias_prev, a.dx, a.u = _p(dbias_prev), _p(dx), _p(u)
+    L.check(lib.simvgb_ln_bwd(ctypes.byref(a), L.c_vp(_stream())), "ln_bwd")
+    _launches[0] += 1
+
+
+def colsum(x, out=None, out_bf16=None, row_scale=None, rows_per_scale=1, C=None, ld=None):
+    lib = _lib_setup()
+    R = x.shape[0]
+    C = C if C is not None else x.shape[1]
+    ld = ld if ld is not None else x.stride(0)
+    L.check(lib.simvgb_colsum(x.data_ptr(), int(x.dtype == bf16), _p(out), _p(out_bf16), _p(row_scale), rows_per_scale,
+                              R, C, ld, _stream()), "colsum")
+    _launches[0] += 1
+    return out
+
+
+def cast_bf16(src, dst):
+    """dst (bf16, same numel, contiguous) = src (fp32, contiguous)."""
+    lib = _lib_setup()
+    L.check(lib.simvgb_cast_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "cast_bf16")
+    _launches[0] += 1
+    return dst
+
+
+def im2col_patch(img, P):
+    L.require_device(img)
+    lib = _lib_setup()
+    B, _, S, _ = img.shape
+    cols = torch.empty(B * (S // P) ** 2, 3 * P * P, device=img.device, dtype=bf16)
+    L.check(lib.simvgb_im2col_patch(img.data_ptr(), cols.data_ptr(), B, S, P, _stream()), "im2col_patch")
+    _launches[0] += 1
+    return cols
+
+
+def embed_vision(patch, cls, posA, B, N, D):
+    lib = _lib_setup()
+    xv = torch.empty(B * (N + 1), D, device=patch.device, dtype=f32)
+    L.check(lib.simvgb_embed_vision(patch.data_ptr(), cls.data_ptr(), posA.data_ptr(), xv.data_ptr(), B, N, D, _stream()),
+            "embed_vision")
+    _launches[0] += 1
+    return xv
+
+
+def embed_text(table, ids, pad, posB, B, Lt, D):
+    lib = _lib_setup()
+    xt = torch.empty(B * Lt, D, device=table.device, dtype=f32)
+    L.check(lib.simvgb_embed_text(table.data_ptr(), ids.data_ptr(), _p(pad), posB.data_ptr(), xt.data_ptr(), B, Lt, D,
+                                  _stream()), "embed_text")
+    _launches[0] += 1
+    return xt
+
+
+def sumsq(g, out):
+    lib = _lib_setup()
+    L.check(lib.simvgb_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "sumsq")
+    _launches[0] += 1
+
+
+def adam_amsgrad(p, g, m, v, vmax, lr, beta1, beta2, eps, weight_decay, step, grad_sumsq=None, max_norm=0.0):
+    lib = _lib_setup()
+    L.check(lib.simvgb_adam_amsgrad(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), vmax.data_ptr(), p.numel(),
+                                    lr, beta1, beta2, eps, weight_decay, step, _p(grad_sumsq), max_norm, _stream()),
+            "adam_amsgrad")
+    _launches[0] += 1

@@ -1,0 +1,297 @@
+"""TextGuidedQuerySelectKDDETRHead — SimVG's dual-branch head with dynamic-weight-balance distillation (DWBD).
+
+Drop-in for the reference's `HEADS` entry (/root/reference/simvg/models/heads/tgqs_kd_detr_head/tgqs_kd_detr_head.py:22-604):
+same constructor kwargs (:24-48), `forward_train / forward_test / inference` signatures (:456,574,577), output-dict keys
+(:443-452), loss keys (:487-509,571) and state-dict keys.  Quirks that change numbers are replicated
+(SURVEY Appendix C): integer-mask text pooling (C.1), the integer-frequency 1-D sine table (C.2), single-Linear token MLP
+with a stacked leading dim (C.5), plain-CE teacher loss in the balanced branch (C.6), detached balance weight (C.7).
+
+What is different from the reference is *how* it runs: the image memory stays token-major [B, N, E] (no NCHW round trip),
+its projections run on the tcgen05 GEMM, position tables are cached per shape instead of rebuilt (and copied H2D) every
+forward, and target preparation / matching for the one-box-per-sample REC case is batched on the device with no host
+synchronisation.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from simvg_b200 import ops
+from simvg_b200.core.box_ops import aligned_iou_giou, box_cxcywh_to_xyxy, box_iou, box_xyxy_to_cxcywh
+from simvg_b200.core.criterion.criterion import HungarianMatcher, SetCriterion
+from simvg_b200.models.builder import HEADS
+from simvg_b200.models.heads.utils import MLP, PositionEmbeddingSine1D
+from simvg_b200.structures import Boxes, Instances
+
+from .transformer import DetrTransformer, DetrTransformerDecoder, DetrTransformerEncoder
+
+
+def _sine_pos_2d(mask, num_pos_feats, temperature=10000, scale=6.283185307179586, eps=1e-6):
+    """detrex PositionEmbeddingSine(normalize=True) emitted token-major: mask [B,h,w] -> [B, h*w, 2*npf]."""
+    not_mask = ~mask
+    y = not_mask.cumsum(1, dtype=torch.float32)
+    x = not_mask.cumsum(2, dtype=torch.float32)
+    y = y / (y[:, -1:, :] + eps) * scale
+    x = x / (x[:, :, -1:] + eps) * scale
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=mask.device)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+    px, py = x[..., None] / dim_t, y[..., None] / dim_t
+    B, h, w = mask.shape
+    px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=4).view(B, h, w, -1)
+    py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), dim=4).view(B, h, w, -1)
+    return torch.cat((py, px), dim=3).view(B, h * w, -1)
+
+
+@HEADS.register_module()
+class TextGuidedQuerySelectKDDETRHead(nn.Module):
+    def __init__(self, num_queries=100, in_channels=768, text_max_token=20, embed_dim=256, num_classes=1, aux_loss=True,
+                 num_encoder_layers=6, num_decoder_layers=6, num_tgqg_layers=1, only_decoder=False, text_embed_aug=False,
+                 branch_loss_weight={}, as_target_query_thr=0.0, distill_type="", decoder_freeze=False,
+                 prepare_target_mode="score_weighted", share_predicthead=False, num_token_mlp_layers=3, mlp_aux_loss=False,
+                 tgqs_mid_dim=512, aux_distill_mode="klloss", text_guided_query_generation=False):
+        super().__init__()
+        assert prepare_target_mode in ["score_weighted", "score_iou_weighted"]
+        assert distill_type in ["hard", "hard_weighted", "soft"]
+        assert all(x in ["decoder", "token", "distill", "merge", "aux_distill", "balanced_distill"] for x in branch_loss_weight)
+        for k in ("merge", "aux_distill"):
+            if k in branch_loss_weight:
+                raise NotImplementedError("branch '%s' is not used by any SimVG config and is outside the hot path" % k)
+        if distill_type == "soft":
+            raise NotImplementedError("distill_type='soft' (mmdet DistillCriterion) is unused by SimVG configs")
+        if decoder_freeze:  # the reference itself raises AttributeError here (tgqs_kd_detr_head.py:186,189; Appendix C.10)
+            raise AttributeError("'TextGuidedQuerySelectKDDETRHead' object has no attribute 'text_guided_query_generation_proj'")
+        self.transformer = DetrTransformer(
+            encoder=DetrTransformerEncoder(embed_dim=embed_dim, num_heads=8, attn_dropout=0.1, feedforward_dim=2048,
+                                           ffn_dropout=0.1, num_layers=num_encoder_layers, post_norm=False),
+            decoder=DetrTransformerDecoder(embed_dim=embed_dim, num_heads=8, attn_dropout=0.1, feedforward_dim=2048,
+                                           ffn_dropout=0.1, num_layers=num_decoder_layers, return_intermediate=True,
+                                           post_norm=True),
+            only_decoder=only_decoder)
+        self.input_proj = nn.Conv2d(in_channels, embed_dim, kernel_size=1)
+        self.input_text_proj = nn.Linear(in_channels, embed_dim)
+        self.input_cls_proj = nn.Linear(in_channels, embed_dim)
+        self.num_queries, self.text_embed_aug, self.as_target_query_thr = num_queries, text_embed_aug, as_target_query_thr
+        self.distill_type, self.prepare_target_mode, self.mlp_aux_loss = distill_type, prepare_target_mode, mlp_aux_loss
+        self.text_guided_query_generation, self.num_token_mlp_layers = text_guided_query_generation, num_token_mlp_layers
+        self.branch_loss_weight, self.num_classes, self.aux_loss, self.embed_dim = branch_loss_weight, num_classes, aux_loss, embed_dim
+        self.position_embedding_1d = PositionEmbeddingSine1D(num_pos_feats=embed_dim // 2, temperature=10000, normalize=True)
+        self.query_embed = nn.Embedding(num_queries, embed_dim)
+        self.mlp = MLP(embed_dim, embed_dim, embed_dim, num_token_mlp_layers, return_intermediate=True) \
+            if num_token_mlp_layers > 0 else nn.Identity()
+        self.class_embed_decoder = nn.Linear(embed_dim, num_classes + 1)
+        self.bbox_embed_decoder = MLP(embed_dim, embed_dim, 4, 3)
+        if share_predicthead:
+            self.class_embed_token, self.bbox_embed_token = self.class_embed_decoder, self.bbox_embed_decoder
+        else:
+            self.class_embed_token = nn.Linear(embed_dim, num_classes + 1)
+            self.bbox_embed_token = MLP(embed_dim, embed_dim, 4, 3)
+        if text_guided_query_generation:
+            self.text_guided_query_generation_transformer = DetrTransformerDecoder(
+                embed_dim=embed_dim, num_heads=8, attn_dropout=0.1, feedforward_dim=tgqs_mid_dim, ffn_dropout=0.1,
+                num_layers=num_tgqg_layers, return_intermediate=False, post_norm=True)
+        self.matcher = HungarianMatcher(cost_class=1, cost_bbox=5.0, cost_giou=2.0, cost_class_type="ce_cost")
+        self.criterion = SetCriterion(num_classes=num_classes, matcher=self.matcher,
+                                      weight_dict={"loss_class": 1, "loss_bbox": 5.0, "loss_giou": 2.0},
+                                      loss_class_type="ce_loss", eos_coef=0.1)
+        if "hard_weighted" in distill_type:
+            self.criterion_harddistill = SetCriterion(num_classes=num_classes, matcher=self.matcher,
+                                                      weight_dict={"loss_class": 1.0, "loss_bbox": 5.0, "loss_giou": 2.0},
+                                                      loss_class_type="weighted_ce_loss", eos_coef=0.1)
+        if aux_loss:  # tgqs_kd_detr_head.py:174-180
+            wd = self.criterion.weight_dict
+            aux = {}
+            for i in range(self.transformer.decoder.num_layers - 1):
+                aux.update({k + "_%d" % i: v for k, v in wd.items()})
+            wd.update(aux)
+        self._pos_cache = {}
+
+    # ------------------------------------------------------------------------------------------ targets
+    @staticmethod
+    def _is_rec(gt_bbox):
+        return all(t.dim() == 1 for t in gt_bbox)
+
+    def prepare_soft_targets(self, targets, decoder_branch_output, img_metas, predict_threahold=0.0,
+                             prepare_target_mode="iou_weighted"):
+        """-> (targets_gt, targets_pred) as lists of per-sample dicts (tgqs_kd_detr_head.py:207-268).  For the REC case
+        everything is computed batched on the device and the per-sample dicts are views."""
+        logits = decoder_branch_output["pred_logits"].detach()
+        boxes = decoder_branch_output["pred_boxes"].detach()
+        scores = F.softmax(logits, dim=-1)[:, :, 0:1]
+        dev = logits.device
+        if self._is_rec(targets):
+            whwh = torch.tensor([[m["img_shape"][1], m["img_shape"][0], m["img_shape"][1], m["img_shape"][0]] for m in img_metas],
+                                dtype=torch.float).to(dev, non_blocking=True)
+            gt = box_xyxy_to_cxcywh(torch.stack([t.to(dev) for t in targets]).float() / whwh).float()  # [B, 4]
+            zeros = torch.zeros(len(targets), 1, dtype=torch.int64, device=dev)
+            new_gt = [{"labels": zeros[i], "boxes": gt[i:i + 1]} for i in range(len(targets))]
+        else:
+            new_gt = []
+            for tb, meta in zip(targets, img_metas):
+                h, w = meta["img_shape"][:2]
+                s = torch.as_tensor([w, h, w, h], dtype=torch.float, device=tb.device)
+                assert int(tb.shape[0]) == len(meta["target"])
+                keep = [i for i, t in enumerate(meta["target"]) if t["category_id"] != -1]
+                tb_ = tb[keep] if keep else torch.zeros((0, 4), device=tb.device)
+                new_gt.append({"labels": torch.zeros(len(keep), device=tb.device).long(),
+                               "boxes": box_xyxy_to_cxcywh(tb_.float() / s).float()})
+        new_pred = []
+        if prepare_target_mode == "score_weighted":
+            for pb, ps in zip(boxes, scores):
+                mask = ps.squeeze(-1) > predict_threahold
+                wgt = torch.zeros_like(ps)
+                wgt[mask] = ps[mask]
+                pb_ = pb[mask, :]
+                new_pred.append({"labels": torch.zeros(pb_.shape[0], device=dev).long(), "boxes": pb_, "weight": wgt})
+        elif prepare_target_mode == "score_iou_weighted":
+            if self._is_rec(targets) and boxes.shape[1] == 1:
+                iou, _ = aligned_iou_giou(box_cxcywh_to_xyxy(boxes[:, 0]), box_cxcywh_to_xyxy(gt))
+                wgt = scores[:, 0, 0] * iou                                               # [B]
+                zeros = torch.zeros(len(targets), 1, dtype=torch.int64, device=dev)
+                new_pred = [{"labels": zeros[i], "boxes": boxes[i], "weight": wgt[i:i + 1]} for i in range(len(targets))]
+            else:
+                indices = self.matcher(decoder_branch_output, new_gt)
+                for (i_p, i_t), pb, ps, tg in zip(indices, boxes, scores, new_gt):
+                    pb_ = pb[i_p]
+                    tg_ = tg["boxes"][i_t]
+                    ious = torch.diag(box_iou(box_cxcywh_to_xyxy(pb_), box_cxcywh_to_xyxy(tg_))[0])
+                    new_pred.append({"labels": torch.zeros(pb_.shape[0], device=dev).long(), "boxes": pb_,
+                                     "weight": ps[i_p].reshape(-1) * ious})
+        else:
+            raise TypeError("{} type is not support yet!! you can choose [score_weighted, iou_weighted] types!!!".format(prepare_target_mode))
+        return new_gt, new_pred
+
+    def _set_aux_loss(self, outputs_class, outputs_coord):
+        return [{"pred_logits": a, "pred_boxes": b} for a, b in zip(outputs_class[:-1], outputs_coord[:-1])]
+
+    def calc_loss(self, output_class, output_coord, targets, criterion=None):
+        """tgqs_kd_detr_head.py:340-350."""
+        criterion = criterion or self.criterion
+        output = {"pred_logits": output_class[-1], "pred_boxes": output_coord[-1]}
+        if self.aux_loss:
+            output["aux_outputs"] = self._set_aux_loss(output_class, output_coord)
+        loss_dict = criterion(output, targets)
+        wd = self.criterion.weight_dict
+        return {k: (v * wd[k] if k in wd else v) for k, v in loss_dict.items()}
+
+    # ------------------------------------------------------------------------------------------ forward
+    def x_mask_pos_enc(self, B, hw, img_metas, device):
+        """Padding mask + 2-D sine positions (tgqs_kd_detr_head.py:322-338), cached per (batch geometry)."""
+        try:
+            ih, iw = img_metas[0]["batch_input_shape"]
+        except Exception:  # noqa: BLE001
+            ih, iw, _ = img_metas[0]["img_shape"]
+        key = (B, hw, ih, iw, tuple(tuple(m["img_shape"][:2]) for m in img_metas), str(device))
+        if key not in self._pos_cache:
+            if len(self._pos_cache) > 16:
+                self._pos_cache.clear()
+            m = torch.ones((B, ih, iw))
+            for i, meta in enumerate(img_metas):
+                h, w = meta["img_shape"][:2]
+                m[i, :h, :w] = 0
+            m = F.interpolate(m.unsqueeze(1), size=hw).to(torch.bool).squeeze(1).to(device)
+            self._pos_cache[key] = (m.view(B, -1), _sine_pos_2d(m, self.embed_dim // 2))
+        return self._pos_cache[key]
+
+    def forward_general(self, x_mm, img_metas, cls_feat=None, text_feat=None, text_mask=None):
+        """x_mm: [B, C, h, w] (any strides; a channels-last view avoids a copy).  tgqs_kd_detr_head.py:375-454."""
+        B, C, h, w = x_mm.shape
+        nq, E = self.num_queries, self.embed_dim
+        mem_in = x_mm.permute(0, 2, 3, 1).reshape(B * h * w, C)
+        memory = ops.linear(mem_in, self.input_proj.weight.view(E, C), self.input_proj.bias).view(B, h * w, E)
+        text_feat = self.input_text_proj(text_feat)
+        cls_feat = self.input_cls_proj(cls_feat).unsqueeze(1)
+        img_masks, pos_embed = self.x_mask_pos_enc(B, (h, w), img_metas, x_mm.device)
+        cls_feat = cls_feat.repeat((1, nq, 1))
+        if self.text_guided_query_generation:
+            # `~text_mask` on the loader's int64 mask is a bitwise NOT -> integer row gather (rows -1 / -2), Appendix C.1
+            inv = ~text_mask
+            if inv.dtype == torch.bool:
+                tff = torch.cat([torch.max(f[m, :], dim=0, keepdim=True)[0] for f, m in zip(text_feat, inv)])
+            else:
+                tff = torch.gather(text_feat, 1, (inv % text_feat.shape[1]).unsqueeze(-1).expand(-1, -1, E)).max(dim=1)[0]
+            tff = tff.unsqueeze(1).repeat(1, nq, 1)
+            qe_in = self.query_embed.weight.unsqueeze(0).repeat(B, 1, 1)
+            tpos = self.position_embedding_1d(text_feat).unsqueeze(0).expand(B, -1, -1)
+            qe = self.text_guided_query_generation_transformer(torch.zeros_like(qe_in), text_feat, text_feat, query_pos=qe_in,
+                                                               key_pos=tpos, key_padding_mask=text_mask.bool())
+            query_embed = qe[0] + tff + qe_in
+            cls_feat = query_embed + cls_feat
+        else:
+            query_embed = self.query_embed.weight.unsqueeze(0).repeat(B, 1, 1)
+        if "decoder" in self.branch_loss_weight and len(self.branch_loss_weight) == 1:
+            token_branch_output = {"pred_logits": None, "pred_boxes": None}
+            cls_tok = coord_tok = None
+        else:
+            cls_feat = self.mlp(cls_feat)
+            if self.num_token_mlp_layers == 0:
+                cls_feat = cls_feat.unsqueeze(0)
+            cls_tok = self.class_embed_token(cls_feat)
+            coord_tok = self.bbox_embed_token(cls_feat).sigmoid()
+            token_branch_output = {"pred_logits": cls_tok[-1], "pred_boxes": coord_tok[-1]}
+        hidden_states = self.transformer(memory, img_masks, query_embed, pos_embed)
+        cls_dec = self.class_embed_decoder(hidden_states)
+        coord_dec = self.bbox_embed_decoder(hidden_states).sigmoid()
+        decoder_branch_output = {"pred_logits": cls_dec[-1], "pred_boxes": coord_dec[-1]}
+        return {"token_branch_output": token_branch_output, "decoder_branch_output": decoder_branch_output,
+                "outputs_class_decoder_branch": cls_dec, "outputs_coord_decoder_branch": coord_dec,
+                "outputs_class_token_branch": cls_tok, "outputs_coord_token_branch": coord_tok,
+                "token_features": cls_feat, "decoder_features": hidden_states}
+
+    def forward_train(self, x_mm, img_metas, cls_feat=None, text_feat=None, gt_bbox=None, text_mask=None):
+        """-> (loss_dict, output)  (tgqs_kd_detr_head.py:456-572)."""
+        device = x_mm.device
+        output = self.forward_general(x_mm, img_metas, cls_feat=cls_feat, text_feat=text_feat, text_mask=text_mask)
+        cls_dec, coord_dec = output["outputs_class_decoder_branch"], output["outputs_coord_decoder_branch"]
+        cls_tok, coord_tok = output["outputs_class_token_branch"], output["outputs_coord_token_branch"]
+        targets_gt, targets_predict = self.prepare_soft_targets(gt_bbox, output["decoder_branch_output"], img_metas,
+                                                                predict_threahold=self.as_target_query_thr,
+                                                                prepare_target_mode=self.prepare_target_mode)
+        zero = lambda: torch.zeros((), device=device)  # noqa: E731
+        l_dec, l_tok, l_kd = zero(), zero(), zero()
+        blw = self.branch_loss_weight
+        loss_dict = {}
+        if "decoder" in blw:
+            l_dec = blw["decoder"] * sum(self.calc_loss(cls_dec, coord_dec, targets_gt).values())
+            loss_dict["loss_dgt"] = l_dec
+
+        def last_only(c, b):
+            if not self.mlp_aux_loss and c.dim() == 4:
+                return c[-1:], b[-1:]
+            return c, b
+
+        if "balanced_distill" in blw:
+            w = torch.mean(torch.cat([t["weight"] for t in targets_predict]))
+            ct, bt = last_only(cls_tok, coord_tok)
+            l_tok = blw["balanced_distill"]["token"] * sum(self.calc_loss(ct, bt, targets_gt).values()) * (1 - w)
+            loss_dict["loss_tgt"] = l_tok
+            l_kd = blw["balanced_distill"]["distill"] * sum(self.calc_loss(ct, bt, targets_predict).values()) * w
+            loss_dict["loss_kd"] = l_kd
+            loss_dict["loss_distill_w"] = w
+        else:
+            if "token" in blw:
+                ct, bt = last_only(cls_tok, coord_tok)
+                l_tok = blw["token"] * sum(self.calc_loss(ct, bt, targets_gt).values())
+                loss_dict["loss_tgt"] = l_tok
+            if "distill" in blw:
+                ct, bt = (cls_tok, coord_tok) if self.mlp_aux_loss else (cls_tok[-1:], coord_tok[-1:])
+                crit = self.criterion_harddistill if self.distill_type == "hard_weighted" else self.criterion
+                l_kd = blw["distill"] * sum(self.calc_loss(ct, bt, targets_predict, criterion=crit).values())
+                loss_dict["loss_kd"] = l_kd
+        loss_dict["loss_total"] = l_dec + l_tok + l_kd
+        return loss_dict, output
+
+    def forward_test(self, x_mm, img_metas, text_feat=None, cls_feat=None, with_bbox=False, with_mask=False, text_mask=None):
+        return self.forward_general(x_mm, img_metas, text_feat=text_feat, cls_feat=cls_feat, text_mask=text_mask)
+
+    def inference(self, box_cls, box_pred, image_sizes):
+        """-> list of Instances with .pred_boxes / .scores / .pred_classes (tgqs_kd_detr_head.py:577-604)."""
+        assert len(box_cls) == len(image_sizes)
+        scores, labels = F.softmax(box_cls, dim=-1)[:, :, :-1].max(-1)
+        results = []
+        for sc, lb, bp, size in zip(scores, labels, box_pred, image_sizes):
+            r = Instances(size)
+            r.pred_boxes = Boxes(box_cxcywh_to_xyxy(bp))
+            r.pred_boxes.scale(scale_x=size[1], scale_y=size[0])
+            r.scores = sc
+            r.pred_classes = lb
+            results.append(r)
+        return results

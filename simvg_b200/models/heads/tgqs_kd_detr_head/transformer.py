@@ -1,0 +1,149 @@
+"""Post-norm DETR decoder used by the object-token branch and by text-guided query generation.
+
+Mirrors the module tree (and therefore the state-dict keys) of
+/root/reference/simvg/models/heads/tgqs_kd_detr_head/transformer.py:93-235 built from detrex's BaseTransformerLayer /
+MultiheadAttention / FFN / TransformerLayerSequence:
+    layers.J.attentions.{0,1}.attn.{in_proj_weight,in_proj_bias,out_proj.*}, layers.J.ffns.0.layers.{0.0,1}.*,
+    layers.J.norms.{0,1,2}.*, post_norm_layer.*
+Layout is batch-first internally ([B, n, E]); the large key/value projections of the image memory ([B*N, E] rows) run on
+the tcgen05 GEMM (simvg_b200.ops.linear), the per-query math (nq is 1..10) is latency-bound and stays in small fp32 ops.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from simvg_b200 import ops
+
+_BIG_ROWS = 4096  # projections with at least this many rows go to the tensor-core GEMM
+
+
+def _proj(x, W, b):
+    if x.is_cuda and x.numel() // x.shape[-1] >= _BIG_ROWS:
+        return ops.linear(x, W, b)
+    return F.linear(x, W, b)
+
+
+class _Attention(nn.Module):
+    """detrex MultiheadAttention wrapper (A.9): positions are added to q/k only, output = identity + attn(...)."""
+
+    def __init__(self, embed_dim, num_heads, attn_drop):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.attn_drop = embed_dim, num_heads, attn_drop
+        self.attn = nn.MultiheadAttention(embed_dim, num_heads, dropout=attn_drop)  # parameter holder (+ its init)
+
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None, key_padding_mask=None):
+        # batch-first: query [B, nq, E], key/value [B, nk, E], key_padding_mask [B, nk] (True = ignore)
+        if key is None:
+            key = query
+        if value is None:
+            value = key
+        if identity is None:
+            identity = query
+        if key_pos is None and query_pos is not None and query_pos.shape == key.shape:
+            key_pos = query_pos
+        q_in = query if query_pos is None else query + query_pos
+        k_in = key if key_pos is None else key + key_pos
+        E, H = self.embed_dim, self.num_heads
+        dh = E // H
+        W, bias = self.attn.in_proj_weight, self.attn.in_proj_bias
+        q = _proj(q_in, W[:E], bias[:E])
+        k = _proj(k_in, W[E:2 * E], bias[E:2 * E])
+        v = _proj(value, W[2 * E:], bias[2 * E:])
+        B, nq, nk = q.shape[0], q.shape[1], k.shape[1]
+        q = q.view(B, nq, H, dh).transpose(1, 2) * (dh ** -0.5)
+        k = k.view(B, nk, H, dh).transpose(1, 2)
+        v = v.view(B, nk, H, dh).transpose(1, 2)
+        s = q @ k.transpose(-1, -2)
+        if key_padding_mask is not None:
+            s = s.masked_fill(key_padding_mask.view(B, 1, 1, nk), float("-inf"))
+        p = F.softmax(s, dim=-1)
+        if self.training and self.attn_drop > 0:
+            p = F.dropout(p, p=self.attn_drop)
+        o = (p @ v).transpose(1, 2).reshape(B, nq, E)
+        o = F.linear(o, self.attn.out_proj.weight, self.attn.out_proj.bias)
+        return identity + o  # proj_drop = 0
+
+
+class _FFN(nn.Module):
+    """detrex FFN (A.9): Linear -> ReLU -> Dropout -> Linear -> Dropout, + identity."""
+
+    def __init__(self, embed_dim, feedforward_dim, ffn_drop):
+        super().__init__()
+        self.layers = nn.Sequential(
+            nn.Sequential(nn.Linear(embed_dim, feedforward_dim), nn.ReLU(inplace=True), nn.Dropout(ffn_drop)),
+            nn.Linear(feedforward_dim, embed_dim), nn.Dropout(ffn_drop))
+
+    def forward(self, x):
+        return x + self.layers(x)
+
+
+class _DecoderLayer(nn.Module):
+    """operation_order = (self_attn, norm, cross_attn, norm, ffn, norm)  (transformer.py:122; A.10)."""
+
+    def __init__(self, embed_dim, num_heads, attn_drop, feedforward_dim, ffn_drop):
+        super().__init__()
+        self.attentions = nn.ModuleList([_Attention(embed_dim, num_heads, attn_drop) for _ in range(2)])
+        self.ffns = nn.ModuleList([_FFN(embed_dim, feedforward_dim, ffn_drop)])
+        self.norms = nn.ModuleList([nn.LayerNorm(embed_dim) for _ in range(3)])
+        self.embed_dim = embed_dim
+
+    def forward(self, query, key, value, query_pos, key_pos, key_padding_mask):
+        query = self.norms[0](self.attentions[0](query, query, query, query_pos=query_pos, key_pos=query_pos))
+        query = self.norms[1](self.attentions[1](query, key, value, query_pos=query_pos, key_pos=key_pos,
+                                                 key_padding_mask=key_padding_mask))
+        return self.norms[2](self.ffns[0](query))
+
+
+class DetrTransformerDecoder(nn.Module):
+    def __init__(self, embed_dim=256, num_heads=8, attn_dropout=0.1, feedforward_dim=2048, ffn_dropout=0.1, num_layers=6,
+                 post_norm=True, return_intermediate=True, batch_first=False):
+        super().__init__()
+        self.layers = nn.ModuleList([_DecoderLayer(embed_dim, num_heads, attn_dropout, feedforward_dim, ffn_dropout)
+                                     for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.return_intermediate = return_intermediate
+        self.embed_dim = embed_dim
+        self.post_norm_layer = nn.LayerNorm(embed_dim) if post_norm else None
+
+    def forward(self, query, key, value, query_pos=None, key_pos=None, key_padding_mask=None):
+        """Batch-first tensors.  Returns [num_layers | 1, B, nq, E]  (transformer.py:134-186: the shared post-norm is
+        applied to every returned intermediate while the un-normed query feeds the next layer)."""
+        inter = []
+        for layer in self.layers:
+            query = layer(query, key, value, query_pos, key_pos, key_padding_mask)
+            if self.return_intermediate:
+                inter.append(self.post_norm_layer(query) if self.post_norm_layer is not None else query)
+        if not self.return_intermediate:
+            if self.post_norm_layer is not None:
+                query = self.post_norm_layer(query)
+            return query[None]
+        return torch.stack(inter)
+
+
+class DetrTransformerEncoder(nn.Module):
+    """Constructed by the reference head and dropped when only_decoder=True (transformer.py:192-194); SimVG never runs
+    it, so only the constructor signature is kept."""
+
+    def __init__(self, embed_dim=256, num_heads=8, attn_dropout=0.1, feedforward_dim=2048, ffn_dropout=0.1, num_layers=6,
+                 post_norm=False, batch_first=False):
+        super().__init__()
+        self.embed_dim, self.num_layers = embed_dim, num_layers
+
+
+class DetrTransformer(nn.Module):
+    def __init__(self, encoder=None, decoder=None, only_decoder=False):
+        super().__init__()
+        if not only_decoder:
+            raise NotImplementedError("SimVG configs use only_decoder=True (the BEiT-3 encoder replaces the DETR encoder)")
+        self.decoder = decoder
+        self.embed_dim = decoder.embed_dim
+        self.only_decoder = only_decoder
+        for p in self.parameters():  # transformer.py:200-203
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    def forward(self, memory, mask, query_embed, pos_embed):
+        """memory / pos_embed: [B, N, E] token-major (the reference's [B,E,h,w] flattened), mask [B, N] bool,
+        query_embed [B, nq, E].  Returns hidden states [layers, B, nq, E]."""
+        target = torch.zeros_like(query_embed)
+        return self.decoder(target, memory, memory, query_pos=query_embed, key_pos=pos_embed, key_padding_mask=mask)
