@@ -64,7 +64,7 @@ def multiway_attention(sd, prefix, x, key_padding_mask, split, H, eps):
     w = q @ k.transpose(-1, -2)
     if key_padding_mask is not None:
         w = w.masked_fill(key_padding_mask.unsqueeze(1).unsqueeze(2).to(torch.bool), float("-inf"))
-    w = F.softmax(w, dim=-1, dtype=torch.float32).type_as(w) if w.dtype != torch.float64 else F.softmax(w, dim=-1)
+    w = F.softmax(w, dim=-1, dtype=torch.float32).type_as(w)   # fp32 softmax whatever the activation dtype (A.4)
     a = (w @ v).transpose(1, 2).reshape(B, L, D)
     a = _mw_ln(sd, prefix + ".inner_attn_ln", a, split, eps)
     return _mw_linear(sd, prefix + ".out_proj", a, split)
@@ -76,7 +76,7 @@ def multiway_ffn(sd, prefix, x, split, eps):
     for which, xx in (("A", x[:, :split]), ("B", x[:, split:])):
         p = "%s.%s." % (prefix, which)
         h = F.linear(xx, sd[p + "fc1.weight"], sd[p + "fc1.bias"])
-        h = F.gelu(h.float()).type_as(h) if h.dtype != torch.float64 else F.gelu(h)
+        h = F.gelu(h.float()).type_as(h)                            # erf GELU evaluated in fp32 (A.5)
         h = F.layer_norm(h, (h.shape[-1],), sd[p + "ffn_layernorm.weight"], sd[p + "ffn_layernorm.bias"], eps)
         outs.append(F.linear(h, sd[p + "fc2.weight"], sd[p + "fc2.bias"]))
     return torch.cat(outs, dim=1)

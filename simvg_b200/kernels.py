@@ -17,6 +17,42 @@ f32 = torch.float32
 _launches = [0]
 
 
+# Optional per-family device timing (bench.py's roofline leg): family -> list of (start event, end event, flops).
+_prof = [None]
+
+
+def profile_start():
+    _prof[0] = {}
+
+
+def profile_stop():
+    """-> {family: (launches, total_ms, total_flops)}; synchronises."""
+    data, _prof[0] = _prof[0], None
+    torch.cuda.synchronize()
+    out = {}
+    for fam, evs in (data or {}).items():
+        out[fam] = (len(evs), sum(a.elapsed_time(b) for a, b, _ in evs), sum(f for _, _, f in evs))
+    return out
+
+
+class _timed:
+    def __init__(self, family, flops):
+        self.family, self.flops = family, flops
+
+    def __enter__(self):
+        if _prof[0] is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _prof[0] is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof[0].setdefault(self.family, []).append((self.e0, e1, self.flops))
+        return False
+
+
 def launch_count():
     return _launches[0]
 
@@ -107,7 +143,8 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, bias=None,
     a.row_scale = _p(row_scale)
     a.rows_per_scale = rows_per_scale
     a.accumulate = int(accumulate)
-    L.check(lib.simvgb_gemm(ctypes.byref(a), L.c_vp(_stream())), "gemm")
+    with _timed("gemm", 2.0 * M * N * K):
+        L.check(lib.simvgb_gemm(ctypes.byref(a), L.c_vp(_stream())), "gemm")
     _launches[0] += 1
     return out
 
@@ -151,7 +188,8 @@ def attn_fwd(qkv_v, qkv_t, pad, B, H, Lv, Lt):
     out_t = torch.empty(B * Lt, D, device=dev, dtype=bf16)
     lse = torch.empty(B, H, attn_lse_stride(Lv, Lt), device=dev, dtype=f32)
     a = _attn_args(B, H, Lv, Lt, qkv_v, qkv_t, pad, out_v, out_t, lse)
-    L.check(lib.simvgb_attn_fwd(ctypes.byref(a), L.c_vp(_stream())), "attn_fwd")
+    with _timed("attn_fwd", 4.0 * B * H * (Lv + Lt) ** 2 * 64):
+        L.check(lib.simvgb_attn_fwd(ctypes.byref(a), L.c_vp(_stream())), "attn_fwd")
     _launches[0] += 1
     return out_v, out_t, lse
 
@@ -174,7 +212,8 @@ def attn_bwd(qkv_v, qkv_t, pad, out_v, out_t, lse, dout_v, dout_t, B, H, Lv, Lt,
     a.dout_v, a.dout_t = _p(dout_v), _p(dout_t)
     a.dqkv_v, a.dqkv_t = _p(dqkv_v), _p(dqkv_t)
     a.delta, a.dq_acc_v, a.dq_acc_t = _p(ws["delta"]), _p(ws["dq_v"]), _p(ws["dq_t"])
-    L.check(lib.simvgb_attn_bwd(ctypes.byref(a), L.c_vp(_stream())), "attn_bwd")
+    with _timed("attn_bwd", 10.0 * B * H * (Lv + Lt) ** 2 * 64):
+        L.check(lib.simvgb_attn_bwd(ctypes.byref(a), L.c_vp(_stream())), "attn_bwd")
     _launches[0] += 5
     return dqkv_v, dqkv_t
 

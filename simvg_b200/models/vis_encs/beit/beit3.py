@@ -150,6 +150,7 @@ class BEIT3(nn.Module):
         self.drop_path_probs = [float(p) for p in np.linspace(0, dpr, L)] if dpr > 0 else [0.0] * L
         self._flat = None
         self._attn_ws = {}
+        self._ddp = None   # set by simvg_b200.optim.FlatDDP: gradient ranges are all-reduced as they become final
         if isinstance(pretrain, str):
             self.load_model_and_may_interpolate(pretrain)
         if freeze_layer >= 0:
@@ -360,6 +361,10 @@ def encoder_backward(mod, ctx, dxv, dxt):
     fb = mod.flat()
     glob, layers = ctx["views"]
     dev = dxv.device
+    ddp = getattr(mod, "_ddp", None)
+    nf = len(_GROUP_FIELDS)
+    if ddp is not None:
+        ddp.on_encoder_backward_start()
     dres = [None, None]
     dyb = [torch.empty(Rs[g], D, device=dev, dtype=bf16) for g in range(2)]
     nl = len(layers)
@@ -413,6 +418,11 @@ def encoder_backward(mod, ctx, dxv, dxt):
                 K.ln_bwd(0, sv["x_in"], dh, G.w["ln1_w"], sv["m1"], sv["r1"], G.g["ln1_w"], G.g["ln1_b"], dres_in=dres[g],
                          dres_out=dres[g])
         ctx["layers"][li] = None  # release this layer's activations
+        if ddp is not None and li > 0:
+            # every gradient of layer li is final now (its fc2 bias was written by layer li+1's LN1 backward)
+            i0 = mod._n_global + li * 2 * nf
+            i1 = i0 + 2 * nf
+            ddp.on_encoder_range_done(fb.offsets[i0], fb.offsets[i1] if i1 < len(fb.offsets) else fb.numel)
     # ---- embeddings (Encoder.forward_embedding, beit3_base.py:317-334 ; VisionEmbedding / TextEmbedding A.6-A.7)
     dv = dres[0].view(B, Lv, D)
     glob["posA"][2][2:2 + Lv].add_(dv.sum(0))
@@ -428,6 +438,9 @@ def encoder_backward(mod, ctx, dxv, dxt):
     for i, p in enumerate(fb.params):
         if not p.requires_grad:
             fb.grad_of(i).zero_()
+    if ddp is not None:   # layer 0 + the embedding / final-LN parameters at the front of the buffer
+        i1 = mod._n_global + 2 * nf
+        ddp.on_encoder_range_done(0, fb.offsets[i1] if i1 < len(fb.offsets) else fb.numel)
 
 
 class _EncoderFn(torch.autograd.Function):

@@ -1,0 +1,217 @@
+"""CPU-side checks: the drop-in boundary (registries, ctor kwargs, state-dict keys), flat parameter storage, the C ABI
+(library loads and exports every symbol include/simvg_b200.h declares), attention tiling geometry, no-fallback policy."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "simvg_b200.h")).read()
+    names = set(re.findall(r"\b(simvgb_[a-z0-9_]+)\s*\(", hdr))
+    assert {"simvgb_gemm", "simvgb_attn_fwd", "simvgb_attn_bwd", "simvgb_ln_fwd", "simvgb_ln_bwd", "simvgb_adam_amsgrad"} <= names
+    for n in sorted(names):
+        assert hasattr(lib, n), "libsimvg_b200.so does not export %s" % n
+    assert lib.simvgb_version() == 100
+
+
+def test_cabi_argument_validation_without_gpu(lib):
+    """Error conventions: <0 + message, no exceptions, no device needed for argument errors."""
+    from simvg_b200 import _lib as L
+    a = L.GemmArgs()
+    a.M, a.N, a.K = 0, 8, 8
+    assert lib.simvgb_gemm(ctypes.byref(a), None) < 0
+    assert b"bad shape" in lib.simvgb_last_error()
+    assert lib.simvgb_gemm(None, None) < 0
+    lib.simvgb_attn_lse_stride.restype = ctypes.c_int
+    assert lib.simvgb_attn_lse_stride(1601, 20) == 13 * 128
+    assert lib.simvgb_attn_lse_stride(401, 20) == 4 * 128
+    assert lib.simvgb_attn_lse_stride(2305, 20) == 19 * 128
+    assert lib.simvgb_attn_lse_stride(256, 20) == 3 * 128
+
+
+def test_product_refuses_cpu_tensors():
+    from simvg_b200 import kernels as K
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        K.ln_fwd(torch.zeros(4, 256), torch.ones(256), torch.zeros(256), 1e-5)
+    from simvg_b200.models import build_model
+    from tools.synth import make_batch, model_cfg
+    m = build_model(model_cfg("base", 64, 32))
+    b = make_batch(1, 64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(b["img"], b["ref_expr_inds"], b["img_metas"], return_loss=False, text_attention_mask=b["text_attention_mask"])
+
+
+def test_registry_builds_reference_config_and_keys():
+    from simvg_b200.models import HEADS, MODELS, VIS_ENCODERS, build_model
+    from tools.synth import model_cfg
+    assert "BEIT3" in VIS_ENCODERS and "TextGuidedQuerySelectKDDETRHead" in HEADS and "MIXDETRMB" in MODELS
+    m = build_model(model_cfg("base", 640, 32))
+    keys = set(m.state_dict().keys())
+    # SURVEY Appendix D
+    expect = ["vis_enc.beit3.text_embed.weight", "vis_enc.beit3.vision_embed.proj.weight", "vis_enc.beit3.vision_embed.mask_token",
+              "vis_enc.beit3.vision_embed.cls_token", "vis_enc.beit3.encoder.embed_positions.A.weight",
+              "vis_enc.beit3.encoder.embed_positions.B.weight", "vis_enc.beit3.encoder.layer_norm.B.bias",
+              "head.input_proj.weight", "head.input_text_proj.bias", "head.input_cls_proj.weight", "head.query_embed.weight",
+              "head.mlp.layers.0.weight", "head.class_embed_decoder.weight", "head.class_embed_token.bias",
+              "head.bbox_embed_decoder.layers.2.weight", "head.bbox_embed_token.layers.0.bias",
+              "head.transformer.decoder.post_norm_layer.weight", "head.text_guided_query_generation_transformer.post_norm_layer.bias",
+              "head.criterion.empty_weight", "head.criterion_harddistill.empty_weight"]
+    for i in (0, 11):
+        for w in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            for ab in "AB":
+                expect += ["vis_enc.beit3.encoder.layers.%d.self_attn.%s.%s.%s" % (i, w, ab, t) for t in ("weight", "bias")]
+        for ab in "AB":
+            expect += ["vis_enc.beit3.encoder.layers.%d.%s.%s.weight" % (i, n, ab) for n in
+                       ("self_attn.inner_attn_ln", "self_attn_layer_norm", "final_layer_norm")]
+            expect += ["vis_enc.beit3.encoder.layers.%d.ffn.%s.%s.%s" % (i, ab, n, t) for n in ("fc1", "fc2", "ffn_layernorm")
+                       for t in ("weight", "bias")]
+    for j in range(3):
+        for a in (0, 1):
+            expect += ["head.transformer.decoder.layers.%d.attentions.%d.attn.%s" % (j, a, t) for t in
+                       ("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias")]
+        expect += ["head.transformer.decoder.layers.%d.ffns.0.layers.0.0.weight" % j,
+                   "head.transformer.decoder.layers.%d.ffns.0.layers.1.bias" % j, "head.transformer.decoder.layers.%d.norms.2.weight" % j]
+    for j in range(2):
+        expect += ["head.text_guided_query_generation_transformer.layers.%d.ffns.0.layers.0.0.weight" % j]
+    missing = [k for k in expect if k not in keys]
+    assert not missing, missing
+    sd = m.state_dict()
+    assert sd["vis_enc.beit3.encoder.embed_positions.A.weight"].shape == (400 + 3, 768)
+    assert sd["vis_enc.beit3.encoder.embed_positions.B.weight"].shape == (1024, 768)
+    assert sd["vis_enc.beit3.vision_embed.proj.weight"].shape == (768, 3, 32, 32)
+    assert sd["head.transformer.decoder.layers.0.ffns.0.layers.0.0.weight"].shape == (2048, 256)
+    assert sd["head.text_guided_query_generation_transformer.layers.0.ffns.0.layers.0.0.weight"].shape == (512, 256)
+    assert sd["head.transformer.decoder.layers.0.attentions.1.attn.in_proj_weight"].shape == (768, 256)
+    assert m.vis_enc.hidden_size == 768 and m.vis_enc.get_num_layers() == 12 and m.fp16_enabled is False
+    assert all("vis_enc" in n for n, _ in m.vis_enc.named_parameters(prefix="vis_enc"))
+    # aux weight dict built from decoder depth (tgqs_kd_detr_head.py:174-180)
+    assert set(m.head.criterion.weight_dict) == {"loss_class", "loss_bbox", "loss_giou", "loss_class_0", "loss_bbox_0",
+                                                 "loss_giou_0", "loss_class_1", "loss_bbox_1", "loss_giou_1"}
+
+
+def test_vit_large_config_and_droppath_quirk():
+    from simvg_b200.models.vis_encs.beit.beit3 import BEIT3
+    with pytest.raises(TypeError):
+        BEIT3(img_size=64, patch_size=32, vit_type="huge", vocab_size=16)
+    base = BEIT3(img_size=64, patch_size=32, vit_type="base", vocab_size=16, drop_path_rate=0.1)
+    assert base.drop_path_probs[0] == 0.0 and abs(base.drop_path_probs[-1] - 0.1) < 1e-12 and len(base.drop_path_probs) == 12
+
+
+def test_flat_buffer_views_grads_and_relocation():
+    from simvg_b200.flat import FlatBuffer
+    lin = torch.nn.Linear(5, 3)
+    ln = torch.nn.LayerNorm(7)
+    params = list(lin.named_parameters()) + list(ln.named_parameters())
+    before = [p.detach().clone() for _, p in params]
+    fb = FlatBuffer(params)
+    assert fb.is_valid()
+    for (n, p), b in zip(params, before):
+        assert torch.equal(p, b)
+        assert p.data_ptr() >= fb.data.data_ptr() and p.data_ptr() % 16 == 0
+    fb.attach_grads()
+    lin(torch.randn(2, 5)).sum().backward()
+    assert lin.weight.grad.data_ptr() == fb.grad_of(0).data_ptr()
+    assert float(fb.grad.abs().sum()) > 0
+    fb.zero_grad()
+    assert float(fb.grad.abs().sum()) == 0
+    lin.weight.data = lin.weight.data.clone()      # what model.to(device) does
+    assert not fb.is_valid()
+    fb.ensure()
+    assert fb.is_valid() and torch.equal(lin.weight, before[0])
+    lin.zero_grad(set_to_none=True)
+    ln.zero_grad(set_to_none=True)
+    fb.attach_grads()
+    assert lin.weight.grad is not None and lin.weight.grad.data_ptr() == fb.grad_of(0).data_ptr()
+
+
+def test_encoder_flat_layout_makes_qkv_contiguous():
+    from simvg_b200.models.vis_encs.beit.beit3 import _GROUP_FIELDS, BEIT3
+    enc = BEIT3(img_size=64, patch_size=32, vit_type="base", vocab_size=32)
+    fb = enc.flat()
+    i = enc._n_global + _GROUP_FIELDS.index("q_w")
+    D = 768
+    assert fb.offsets[i + 1] - fb.offsets[i] == D * D and fb.offsets[i + 2] - fb.offsets[i + 1] == D * D
+    sa = enc.beit3.encoder.layers[0].self_attn
+    w = fb.data[fb.offsets[i]:fb.offsets[i] + 3 * D * D].view(3 * D, D)
+    assert torch.equal(w[:D], sa.q_proj.A.weight) and torch.equal(w[D:2 * D], sa.k_proj.A.weight) and torch.equal(w[2 * D:], sa.v_proj.A.weight)
+    # state-dict round trip keeps the views
+    sd = {k: v.clone() + 1 for k, v in enc.state_dict().items()}
+    enc.load_state_dict(sd)
+    assert fb.is_valid() and torch.equal(w[:D], sd["beit3.encoder.layers.0.self_attn.q_proj.A.weight"])
+
+
+def test_criterion_matches_oracle_on_cpu():
+    """The product's SetCriterion / matcher / target preparation are plain PyTorch: check them against the oracle here."""
+    from oracle import simvg_oracle as O
+    from simvg_b200.core.criterion.criterion import HungarianMatcher, SetCriterion
+    torch.manual_seed(0)
+    for nq in (1, 7):
+        B = 4
+        logits = torch.randn(3, B, nq, 2)
+        boxes = torch.rand(3, B, nq, 4) * 0.4 + 0.2
+        tg = [{"labels": torch.zeros(1, dtype=torch.int64), "boxes": torch.rand(1, 4) * 0.3 + 0.3} for _ in range(B)]
+        crit = SetCriterion(1, HungarianMatcher(1, 5.0, 2.0, "ce_cost"), {"loss_class": 1, "loss_bbox": 5.0, "loss_giou": 2.0},
+                            loss_class_type="ce_loss", eos_coef=0.1)
+        out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1],
+               "aux_outputs": [{"pred_logits": a, "pred_boxes": b} for a, b in zip(logits[:-1], boxes[:-1])]}
+        got = crit(out, tg)
+        want = O.set_criterion(out, tg)
+        assert set(got) == set(want)
+        for k in want:
+            assert torch.allclose(got[k], want[k], rtol=1e-6, atol=1e-7), (nq, k)
+
+
+def test_get_predictions_matches_oracle_on_cpu():
+    from oracle import simvg_oracle as O
+    from simvg_b200.models.det_seg.mix_detr_mb import MIXDETRMB
+    torch.manual_seed(1)
+    metas = [dict(img_shape=(320, 480, 3), scale_factor=[1, 1, 1, 1]) for _ in range(5)]
+    for nq in (1, 6):
+        out = {"pred_logits": torch.randn(5, nq, 2), "pred_boxes": torch.rand(5, nq, 4) * 0.5 + 0.25}
+        got = MIXDETRMB.get_predictions(None, out, metas)
+        want = O.get_predictions(out, metas)
+        assert torch.allclose(got["pred_bboxes"], want["pred_bboxes"], atol=1e-4)
+        assert torch.equal(got["predict_classes"], want["predict_classes"])
+
+
+def test_head_cpu_forward_matches_oracle_small():
+    """Head wiring (TGQG, token branch, decoder branch, DWBD losses) on CPU tensors small enough to stay off the GEMM path."""
+    import copy
+    from oracle import simvg_oracle as O
+    from simvg_b200.models.heads.tgqs_kd_detr_head import transformer as T
+    from simvg_b200.models.heads.tgqs_kd_detr_head.tgqs_kd_detr_head import TextGuidedQuerySelectKDDETRHead
+    from tools.synth import make_batch, model_cfg, synth_state_dict
+    import simvg_b200.ops as ops
+    hc = copy.deepcopy(model_cfg("base", 64, 32)["head"])
+    hc["in_channels"] = 128
+    hc.pop("type")
+    head = TextGuidedQuerySelectKDDETRHead(**copy.deepcopy(hc)).eval()
+    sd = synth_state_dict({k: v.float() for k, v in head.state_dict().items()}, seed=5)
+    head.load_state_dict(sd)
+    old = ops.linear
+    ops.linear = lambda x, W, b=None: torch.nn.functional.linear(x, W, b)   # CPU stand-in for the GEMM in THIS TEST ONLY
+    try:
+        B = 3
+        g = torch.Generator().manual_seed(2)
+        x_mm = torch.randn(B, 128, 2, 2, generator=g)
+        text, cls = torch.randn(B, 20, 128, generator=g), torch.randn(B, 128, generator=g)
+        batch = make_batch(B, 64, seed=3)
+        metas = batch["img_metas"]
+        for m in metas:
+            m["batch_input_shape"] = (64, 64)
+        losses, out = head.forward_train(x_mm, metas, cls_feat=cls, text_feat=text, gt_bbox=batch["gt_bbox"],
+                                         text_mask=batch["text_attention_mask"])
+    finally:
+        ops.linear = old
+    ol, oo = O.head_forward_train({"head." + k: v for k, v in sd.items()}, hc, x_mm, copy.deepcopy(metas), cls, text,
+                                  batch["gt_bbox"], batch["text_attention_mask"])
+    for k in ol:
+        assert torch.allclose(losses[k], ol[k], rtol=2e-5, atol=1e-6), (k, float(losses[k]), float(ol[k]))
+    assert torch.allclose(out["outputs_coord_decoder_branch"], oo["outputs_coord_decoder_branch"], atol=1e-5)
+    assert torch.allclose(out["outputs_coord_token_branch"], oo["outputs_coord_token_branch"], atol=1e-5)
+    assert T._BIG_ROWS > 0

@@ -39,3 +39,29 @@ def model_cfg(vit_type="base", img_size=640, patch_size=16, num_decoder_layers=3
                   text_embed_aug=False, branch_loss_weight=branch_loss_weight, distill_type="hard_weighted",
                   prepare_target_mode="score_iou_weighted", share_predicthead=False, num_token_mlp_layers=1,
                   mlp_aux_loss=False, text_guided_query_generation=True, num_tgqg_layers=2))
+
+
+def synth_state_dict(template, seed):
+    """Deterministic, well-conditioned weights for every floating tensor of `template` (name -> tensor), derived from
+    (seed, name) only — so fixtures store no weights: the reference-over-shims run, the oracle and the CUDA product all
+    regenerate identical parameters.  Matrices ~ N(0, 0.25/fan_in), LayerNorm gains ~ 1 + 0.1 N(0,1), biases ~ 0.05 N(0,1)."""
+    import zlib
+    out = {}
+    for name in sorted(template):
+        t = template[name]
+        if not t.dtype.is_floating_point or "empty_weight" in name:
+            out[name] = t.clone()
+            continue
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 31))
+        r = torch.randn(t.shape, generator=g, dtype=torch.float32)
+        if t.dim() >= 2:
+            fan_in = 1
+            for s in t.shape[1:]:
+                fan_in *= s
+            v = r * (0.5 / max(fan_in, 1) ** 0.5)
+        elif name.endswith("weight"):
+            v = 1.0 + 0.1 * r
+        else:
+            v = 0.05 * r
+        out[name] = v.to(t.dtype)
+    return out
