@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsimvg_b200.so")
+LIB_PATH = os.environ.get("SIMVGB_LIB") or os.path.join(_HERE, "libsimvg_b200.so")   # SIMVGB_LIB: A/B builds when tuning
 _lib = None
 
 c_int, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p

@@ -11,7 +11,10 @@
 // All five products are tcgen05.mma with accumulators in TMEM (S, dP: 128 columns each; dV, dK, dQ: 64 each).
 // P and dS are written once to 128B-swizzled smem by the compute threads and consumed twice: K-major (dQ = dS K)
 // and MN-major (P^T dO, dS^T Q) — the same bytes, two descriptors — so nothing is transposed.
-// Warp roles: 0 TMA producer, 1 MMA issuer, 2-5 compute (one thread per query row), 6-9 dQ write-back.
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2-9 compute (two warps per TMEM lane quarter, 64 key columns each — two
+// resident warps per SM sub-partition hide each other's MUFU/TMEM latency), 10-13 dQ write-back.
+#include <stdlib.h>
+
 #include "attn_common.cuh"
 #include "simvg_b200.h"
 
@@ -20,8 +23,14 @@ namespace simvgb {
 int make_attn_maps(CUtensorMap* full, CUtensorMap* tail, CUtensorMap* text, const AttnGeom& g, const void* base_v,
                    const void* base_t, int row_elems);
 
-constexpr int kBwdThreads = 320;
-constexpr int kBwdSmem = 10 * kTileBytes + 1024 + 256;
+constexpr int kBwdThreads = 448;
+constexpr int kComputeThreads = 256;
+#ifndef SIMVGB_BWD_STAGES
+#define SIMVGB_BWD_STAGES 2
+#endif
+constexpr int kQS = SIMVGB_BWD_STAGES;   // Q_i / dO_i ring depth (TMA latency is ~1.5 us: 2 stages cannot hide it)
+constexpr int kBwdTiles = 2 + 2 * kQS + 8;   // K, V, Q[kQS], dO[kQS], P[2](2 sub-tiles), dS[2](2 sub-tiles)
+constexpr int kBwdSmem = kBwdTiles * kTileBytes + 1024 + 256;
 constexpr float kLog2eB = 1.4426950408889634f;
 
 struct AttnBwdParams {
@@ -33,7 +42,11 @@ struct AttnBwdParams {
   bf16* dqkv_t;
   float* dq_acc_v;
   float* dq_acc_t;
+  int dbg;   // timing ablations (SIMVGB_ATTN_DEBUG); 0 in production
+  long long* ts;   // optional clock64 trace of CTA (0,0,0): [pair][16]
 };
+
+static long long* g_attn_trace = nullptr;
 
 struct AttnMaps6 {
   CUtensorMap qkv_full, qkv_tail, qkv_text, do_full, do_tail, do_text;
@@ -49,21 +62,21 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = smem + kTileBytes;
-  uint8_t* sQ = smem + 2 * kTileBytes;    // [2]
-  uint8_t* sdO = smem + 4 * kTileBytes;   // [2]
-  uint8_t* sP = smem + 6 * kTileBytes;    // 2 sub-tiles
-  uint8_t* sdS = smem + 8 * kTileBytes;   // 2 sub-tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * kTileBytes);
+  uint8_t* sQ = smem + 2 * kTileBytes;                 // [kQS]
+  uint8_t* sdO = smem + (2 + kQS) * kTileBytes;        // [kQS]
+  uint8_t* sP = smem + (2 + 2 * kQS) * kTileBytes;     // [2 buffers][2 sub-tiles]
+  uint8_t* sdS = smem + (6 + 2 * kQS) * kTileBytes;    // [2 buffers][2 sub-tiles]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdTiles * kTileBytes);
   uint64_t* kv_full = bars;
-  uint64_t* qdo_full = bars + 1;    // [2]
-  uint64_t* qdo_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_empty = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* pds_done = bars + 8;
-  uint64_t* dq_full = bars + 9;
-  uint64_t* dq_empty = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* qdo_full = bars + 1;           // [kQS]
+  uint64_t* qdo_empty = bars + 1 + kQS;    // [kQS]
+  uint64_t* s_full = bars + 1 + 2 * kQS;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* pds_done = s_full + 3;
+  uint64_t* dq_full = s_full + 4;
+  uint64_t* dq_empty = s_full + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
   uint32_t* kmask = tmem_slot + 2;  // [4]
 
   const AttnGeom& g = p.g;
@@ -75,17 +88,17 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
   {
     uint4* z = reinterpret_cast<uint4*>(smem);
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < 10 * kTileBytes / 16; i += kBwdThreads) z[i] = zero;
+    for (int i = threadIdx.x; i < kBwdTiles * kTileBytes / 16; i += kBwdThreads) z[i] = zero;
   }
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 2);   // K_j and V_j arrive separately
-    for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 2); mbar_init(&qdo_empty[s], 1); }  // Q_i + dO_i
+    for (int s = 0; s < kQS; ++s) { mbar_init(&qdo_full[s], 2); mbar_init(&qdo_empty[s], 1); }  // Q_i + dO_i
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_empty, kComputeThreads / 32);   // one elected arrival per compute warp
+    mbar_init(p_full, kComputeThreads / 32);
     mbar_init(pds_done, 1);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 128);
+    mbar_init(dq_empty, 4);
     fence_barrier_init();
   }
   if (threadIdx.x == 64) {
@@ -100,7 +113,7 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (uniform registers for UTCHMMA)
   const uint32_t tmS = tmem, tmdP = tmem + 128, tmdV = tmem + 256, tmdK = tmem + 320, tmdQ = tmem + 384;
 
   if (warp == 0) {
@@ -109,8 +122,8 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       // K_j and V_j share one barrier (two expect_tx arrivals, init count 2); likewise Q_i and dO_i.
       load_virtual_tile(sK, kv_full, g, &maps.qkv_full, &maps.qkv_tail, &maps.qkv_text, kt, colk, b);
       for (int i = 0; i < nq; ++i) {
-        const int s = i & 1;
-        mbar_wait(&qdo_empty[s], ((i >> 1) & 1) ^ 1);
+        const int s = i % kQS;
+        mbar_wait(&qdo_empty[s], ((i / kQS) & 1) ^ 1);
         load_virtual_tile(sQ + s * kTileBytes, &qdo_full[s], g, &maps.qkv_full, &maps.qkv_tail, &maps.qkv_text, i,
                           colq, b);
         if (i == 0) load_virtual_tile(sV, kv_full, g, &maps.qkv_full, &maps.qkv_tail, &maps.qkv_text, kt, colv, b);
@@ -119,112 +132,158 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      const uint32_t idesc_dq = umma_idesc_bf16(128, kHeadDim, 0, 1);   // A = dS K-major, B = K_j MN-major
-      const uint32_t idesc_dkv = umma_idesc_bf16(128, kHeadDim, 1, 1);  // A = P^T / dS^T MN-major, B = dO / Q MN-major
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
-      auto issue_sdp = [&](int i) {
-        const int s = i & 1;
-        mbar_wait(&qdo_full[s], (i >> 1) & 1);
-        tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ + s * kTileBytes), do_addr = smem_u32(sdO + s * kTileBytes);
+    // MMA issuer: warp-uniform control flow, single-lane issue (keeps descriptors in uniform registers).
+    const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_dq = umma_idesc_bf16(128, kHeadDim, 0, 1);   // A = dS K-major, B = K_j MN-major
+    const uint32_t idesc_dkv = umma_idesc_bf16(128, kHeadDim, 1, 1);  // A = P^T / dS^T MN-major, B = dO / Q MN-major
+    const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+    const uint64_t dK_kmaj = umma_smem_desc(k_addr, 16, 1024), dV_kmaj = umma_smem_desc(v_addr, 16, 1024);
+    const uint64_t dK_mn = umma_smem_desc(k_addr, 8192, 1024);
+    const uint64_t dP_mn0 = umma_smem_desc(smem_u32(sP), kTileBytes, 1024), dS_mn0 = umma_smem_desc(smem_u32(sdS), kTileBytes, 1024);
+    const uint64_t dS_kmaj0 = umma_smem_desc(smem_u32(sdS), 16, 1024);
+    const uint64_t dQ_kmaj0 = umma_smem_desc(smem_u32(sQ), 16, 1024), dO_kmaj0 = umma_smem_desc(smem_u32(sdO), 16, 1024);
+    const uint64_t dQ_mn0 = umma_smem_desc(smem_u32(sQ), 8192, 1024), dO_mn0 = umma_smem_desc(smem_u32(sdO), 8192, 1024);
+    constexpr uint32_t kTileStep = kTileBytes >> 4;   // descriptor start-address units per 16 KB tile
+    auto issue_sdp = [&](int i) {
+      const int s = i % kQS;
+      mbar_wait(&qdo_full[s], (i / kQS) & 1);
+      tc_fence_after();
+      const uint64_t dq = dQ_kmaj0 + s * kTileStep, dd = dO_kmaj0 + s * kTileStep;
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmS, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024),
-                      idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmS, dq + 2 * k, dK_kmaj + 2 * k, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmdP, umma_smem_desc(do_addr + k * 32, 16, 1024), umma_smem_desc(v_addr + k * 32, 16, 1024),
-                      idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmdP, dd + 2 * k, dV_kmaj + 2 * k, idesc_s, k > 0);
         umma_commit(s_full);
-      };
-      mbar_wait(kv_full, 0);
-      issue_sdp(0);
-      for (int i = 0; i < nq; ++i) {
-        const int s = i & 1;
-        mbar_wait(s_empty, i & 1);
-        if (i + 1 < nq) issue_sdp(i + 1);
-        mbar_wait(p_full, i & 1);
-        if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);
-        tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ + s * kTileBytes), do_addr = smem_u32(sdO + s * kTileBytes);
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    issue_sdp(0);
+    const bool trace = p.ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+    for (int i = 0; i < nq; ++i) {
+      const int s = i % kQS;
+      const int pb = i & 1;   // P / dS buffer of this pair
+      mbar_wait(s_empty, i & 1);
+      if (trace) p.ts[i * 16 + 0] = clock64();
+      if (i + 1 < nq) issue_sdp(i + 1);
+      if (trace) p.ts[i * 16 + 1] = clock64();
+      mbar_wait(p_full, i & 1);
+      if (trace) p.ts[i * 16 + 2] = clock64();
+      if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);
+      if (trace) p.ts[i * 16 + 3] = clock64();
+      tc_fence_after();
+      const uint64_t dsk = dS_kmaj0 + pb * 2 * kTileStep, dsm = dS_mn0 + pb * 2 * kTileStep, dpm = dP_mn0 + pb * 2 * kTileStep;
+      const uint64_t dqm = dQ_mn0 + s * kTileStep, dom = dO_mn0 + s * kTileStep;
+      if (!(p.dbg & 16) && elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // dQ_i = dS K_j
-          umma_f16_ss(tmdQ, umma_smem_desc(ds_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
-                      umma_smem_desc(k_addr + k * 2048, 8192, 1024), idesc_dq, k > 0);
-        umma_commit(dq_full);
+        for (int k = 0; k < 8; ++k)   // dQ_i = dS K_j        (A: dS K-major, B: K_j MN-major)
+          umma_f16_ss(tmdQ, dsk + (k >> 2) * kTileStep + (k & 3) * 2, dK_mn + k * 128, idesc_dq, k > 0);
+      }
+      if (elect_one()) umma_commit(dq_full);
+      if (!(p.dbg & 16) && elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // dV_j += P^T dO_i
-          umma_f16_ss(tmdV, umma_smem_desc(p_addr + k * 2048, kTileBytes, 1024),
-                      umma_smem_desc(do_addr + k * 2048, 8192, 1024), idesc_dkv, (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)   // dV_j += P^T dO_i     (A: P MN-major, B: dO_i MN-major)
+          umma_f16_ss(tmdV, dpm + k * 128, dom + k * 128, idesc_dkv, (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // dK_j += dS^T Q_i
-          umma_f16_ss(tmdK, umma_smem_desc(ds_addr + k * 2048, kTileBytes, 1024),
-                      umma_smem_desc(q_addr + k * 2048, 8192, 1024), idesc_dkv, (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)   // dK_j += dS^T Q_i     (A: dS MN-major, B: Q_i MN-major)
+          umma_f16_ss(tmdK, dsm + k * 128, dqm + k * 128, idesc_dkv, (i > 0 || k > 0) ? 1u : 0u);
+      }
+      if (elect_one()) {
         umma_commit(&qdo_empty[s]);
         umma_commit(pds_done);
       }
+      __syncwarp();
+      if (trace) p.ts[i * 16 + 4] = clock64();
     }
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ------------------------------ compute: P and dS ------------------------------
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;      // key columns [64*half, 64*half + 64)
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
     const float* lse = p.lse + ((long long)b * g.H + h) * lse_stride;
     const float* delta = p.delta + ((long long)b * g.H + h) * lse_stride;
+    const bool ktile_masked = kt >= g.nfull;
     for (int i = 0; i < nq; ++i) {
       const int qv = i * kTile + r;
       const bool row_ok = (qv < g.Lv) || (qv >= g.T0 && qv < g.T0 + g.Lt);
       const float L = row_ok ? __ldg(lse + qv) : 0.f;
       const float dl = row_ok ? __ldg(delta + qv) : 0.f;
+      const bool slow = ktile_masked || (i >= g.nfull);   // warp-uniform: only tail tiles need masking
+      const bool trace = p.ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
+      if (trace) p.ts[i * 16 + 8] = clock64();
       mbar_wait(s_full, i & 1);
-      if (i > 0) mbar_wait(pds_done, (i - 1) & 1);
+      if (trace) p.ts[i * 16 + 9] = clock64();
+      if (i > 1) mbar_wait(pds_done, i & 1);   // MMAs of pair i-2 have finished reading this P/dS buffer
+      if (trace) p.ts[i * 16 + 10] = clock64();
+      const uint32_t aP = smem_u32(sP) + (i & 1) * 2 * kTileBytes;
+      const uint32_t adS = smem_u32(sdS) + (i & 1) * 2 * kTileBytes;
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t sv[32], dv[32];
-        tmem_ld32(tmS + lane_base + c * 32, sv);
-        tmem_ld32(tmdP + lane_base + c * 32, dv);
-        tmem_wait_ld();
-        const uint32_t bits = row_ok ? kmask[c] : 0u;
-        float pr[32], ds[32];
+        if (!(p.dbg & 4)) {
+          tmem_ld32(tmS + lane_base + c * 32, sv);
+          tmem_ld32(tmdP + lane_base + c * 32, dv);
+          tmem_wait_ld();
+        } else {
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const float pv = (bits >> t) & 1u ? exp2f(fmaf(__uint_as_float(sv[t]), kLog2eB, -L)) : 0.f;
-          pr[t] = pv;
-          ds[t] = pv * (__uint_as_float(dv[t]) - dl);
+          for (int t = 0; t < 32; ++t) { sv[t] = 0; dv[t] = 0; }
+        }
+        float pr[32], ds[32];
+        if (p.dbg & 2) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) { pr[t] = __uint_as_float(sv[t]); ds[t] = __uint_as_float(dv[t]); }
+        } else if (!slow) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const float pv = ex2_approx(fmaf(__uint_as_float(sv[t]), kLog2eB, -L));
+            pr[t] = pv;
+            ds[t] = pv * (__uint_as_float(dv[t]) - dl);
+          }
+        } else {
+          const uint32_t bits = row_ok ? kmask[c] : 0u;
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const float pv = (bits >> t) & 1u ? ex2_approx(fmaf(__uint_as_float(sv[t]), kLog2eB, -L)) : 0.f;
+            pr[t] = pv;
+            ds[t] = pv * (__uint_as_float(dv[t]) - dl);
+          }
         }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           const uint32_t off = swz_off(r, c * 4 + q4);
-          *reinterpret_cast<uint4*>(sP + off) =
-              make_uint4(pack_bf16x2(pr[8 * q4], pr[8 * q4 + 1]), pack_bf16x2(pr[8 * q4 + 2], pr[8 * q4 + 3]),
-                         pack_bf16x2(pr[8 * q4 + 4], pr[8 * q4 + 5]), pack_bf16x2(pr[8 * q4 + 6], pr[8 * q4 + 7]));
-          *reinterpret_cast<uint4*>(sdS + off) =
-              make_uint4(pack_bf16x2(ds[8 * q4], ds[8 * q4 + 1]), pack_bf16x2(ds[8 * q4 + 2], ds[8 * q4 + 3]),
-                         pack_bf16x2(ds[8 * q4 + 4], ds[8 * q4 + 5]), pack_bf16x2(ds[8 * q4 + 6], ds[8 * q4 + 7]));
+          st_shared_v4(aP + off, pack_bf16x2(pr[8 * q4], pr[8 * q4 + 1]), pack_bf16x2(pr[8 * q4 + 2], pr[8 * q4 + 3]),
+                       pack_bf16x2(pr[8 * q4 + 4], pr[8 * q4 + 5]), pack_bf16x2(pr[8 * q4 + 6], pr[8 * q4 + 7]));
+          st_shared_v4(adS + off, pack_bf16x2(ds[8 * q4], ds[8 * q4 + 1]), pack_bf16x2(ds[8 * q4 + 2], ds[8 * q4 + 3]),
+                       pack_bf16x2(ds[8 * q4 + 4], ds[8 * q4 + 5]), pack_bf16x2(ds[8 * q4 + 6], ds[8 * q4 + 7]));
         }
       }
+      if (trace) p.ts[i * 16 + 11] = clock64();
       tc_fence_before();
-      mbar_arrive(s_empty);
-      fence_proxy_async();
-      mbar_arrive(p_full);
+      fence_proxy_async();   // this thread's P/dS stores -> async proxy
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(s_empty);
+        mbar_arrive(p_full);
+      }
+      if (trace) p.ts[i * 16 + 12] = clock64();
     }
-    // dK_j -> dqkv[:, D + h*64 ...]
+    // dK_j -> dqkv[:, D + h*64 ...]   (each of the two warps of a quarter stores one 32-column half)
     mbar_wait(pds_done, (nq - 1) & 1);
     tc_fence_after();
     const int kv = kt * kTile + r;
     bf16* dst = nullptr;
     if (kv < g.Lv) dst = p.dqkv_v + ((long long)b * g.Lv + kv) * (3 * g.D) + g.D + h * kHeadDim;
     else if (kv >= g.T0 && kv < g.T0 + g.Lt) dst = p.dqkv_t + ((long long)b * g.Lt + (kv - g.T0)) * (3 * g.D) + g.D + h * kHeadDim;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t v[32];
-      tmem_ld32(tmdK + lane_base + c * 32, v);
+      tmem_ld32(tmdK + lane_base + half * 32, v);
       tmem_wait_ld();
       if (dst != nullptr) {
-        uint4* o = reinterpret_cast<uint4*>(dst + c * 32);
+        uint4* o = reinterpret_cast<uint4*>(dst + half * 32);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
           o[q4] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * q4]), __uint_as_float(v[8 * q4 + 1])),
@@ -251,8 +310,9 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       tmem_ld32(tmdQ + lane_base + 32, v1);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(dq_empty);
-      if (dst != nullptr) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
+      if (dst != nullptr && !(p.dbg & 1)) {
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4)
           red_add_v4(dst + 4 * q4, __uint_as_float(v0[4 * q4]), __uint_as_float(v0[4 * q4 + 1]),
@@ -356,6 +416,11 @@ extern "C" int simvgb_attn_bwd(const simvgb_attn_args* a, void* stream) {
   p.dqkv_t = reinterpret_cast<bf16*>(a->dqkv_t);
   p.dq_acc_v = a->dq_acc_v;
   p.dq_acc_t = a->dq_acc_t;
+  {
+    const char* e = getenv("SIMVGB_ATTN_DEBUG");
+    p.dbg = e ? atoi(e) : 0;
+    p.ts = g_attn_trace;
+  }
   const int lse_stride = p.g.ntiles * kTile;
   AttnMaps6 maps;
   if (make_attn_maps(&maps.qkv_full, &maps.qkv_tail, &maps.qkv_text, p.g, a->qkv_v, a->qkv_t, 3 * D)) return -1;
@@ -397,3 +462,5 @@ extern "C" int simvgb_attn_bwd(const simvgb_attn_args* a, void* stream) {
   SIMVGB_CUDA(cudaGetLastError());
   return 0;
 }
+
+extern "C" void simvgb_debug_attn_trace(long long* buf) { simvgb::g_attn_trace = buf; }

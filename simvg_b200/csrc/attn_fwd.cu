@@ -6,7 +6,9 @@
 // epilogue, matching `q *= self.scaling` after the bias add).
 //
 // One CTA = one 128-query tile of one (b, h); two CTAs are co-resident per SM so one CTA's softmax overlaps the other's
-// MMAs.  Warp roles:  0 = TMA producer, 1 = tcgen05.mma issuer, 2-5 = softmax (one thread per query row).
+// MMAs.  Warp roles:  0 = TMA producer, 1 = tcgen05.mma issuer, 2-9 = softmax: two warps per TMEM lane quarter, each
+// thread owns one query row x 64 key columns (row max exchanged through smem) so every SM sub-partition always has
+// several softmax warps to switch between while MUFU / TMEM loads are in flight.
 //   S = Q K_j^T   : tcgen05.mma M=128 N=128 K=64, both operands K-major, S in TMEM columns [0,128)
 //   O += P V_j    : P (bf16) written by the softmax threads into 128B-swizzled smem, V_j read MN-major straight
 //                   from its token-major TMA tile; O in TMEM columns [128,192)
@@ -16,9 +18,10 @@
 
 namespace simvgb {
 
-constexpr int kFwdThreads = 192;
+constexpr int kFwdThreads = 320;
+constexpr int kSoftmaxThreads = 256;
 constexpr int kSlots = 3;  // K/V ring: K_j, V_j, K_{j+1} ...
-constexpr int kFwdSmem = kTileBytes /*Q*/ + 2 * kTileBytes /*P*/ + kSlots * kTileBytes + 1024 + 256;
+constexpr int kFwdSmem = kTileBytes /*Q*/ + 2 * kTileBytes /*P*/ + kSlots * kTileBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*row-max exchange*/;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnFwdParams {
@@ -28,6 +31,10 @@ struct AttnFwdParams {
   bf16* out_t;               // [B*Lt, D]
   float* lse;                // [B, H, ntiles*128]  log2-domain logsumexp of each query row
 };
+
+__device__ __forceinline__ void pair_sync(int quarter) {   // the two softmax warps that share a TMEM lane quarter
+  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+}
 
 __global__ void __launch_bounds__(kFwdThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_constant__ CUtensorMap map_tail,
@@ -47,6 +54,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   uint64_t* pv_done = s_full + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
   uint32_t* masks = tmem_slot + 2;            // [2][4] validity bits of the (at most two) partial tiles
+  float* xchg = reinterpret_cast<float*>(smem + (3 + kSlots) * kTileBytes + 256);  // [2 parity][2 halves][128 rows]
 
   const AttnGeom& g = p.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -63,8 +71,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
     mbar_init(q_full, 1);
     for (int s = 0; s < kSlots; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 1); }
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_empty, kSoftmaxThreads / 32);   // one elected arrival per softmax warp
+    mbar_init(p_full, kSoftmaxThreads / 32);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -80,7 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (uniform registers for UTCHMMA)
   const uint32_t tmS = tmem, tmO = tmem + 128;
 
   if (warp == 0) {
@@ -96,115 +104,129 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      const uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);  // A = P (K-major), B = V (MN-major)
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-      auto issue_s = [&](int j) {
-        const int n = 2 * j, slot = n % kSlots;
-        mbar_wait(&slot_full[slot], (n / kSlots) & 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sKV + slot * kTileBytes);
+    // MMA issuer: warp-uniform control flow, single-lane issue (keeps descriptors in uniform registers).
+    const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);  // A = P (K-major), B = V (MN-major)
+    const uint64_t dQ = umma_smem_desc(smem_u32(sQ), 16, 1024), dP = umma_smem_desc(smem_u32(sP), 16, 1024);
+    const uint64_t dKV_k = umma_smem_desc(smem_u32(sKV), 16, 1024), dKV_mn = umma_smem_desc(smem_u32(sKV), 8192, 1024);
+    auto issue_s = [&](int j) {
+      const int n = 2 * j, slot = n % kSlots;
+      mbar_wait(&slot_full[slot], (n / kSlots) & 1);
+      tc_fence_after();
+      const uint64_t dk = dKV_k + slot * (kTileBytes >> 4);
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kHeadDim / 16; ++k)
-          umma_f16_ss(tmS, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024),
-                      idesc_s, k > 0);
+        for (int k = 0; k < kHeadDim / 16; ++k) umma_f16_ss(tmS, dQ + 2 * k, dk + 2 * k, idesc_s, k > 0);
         umma_commit(&slot_empty[slot]);
         umma_commit(s_full);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < nk; ++j) {
-        mbar_wait(s_empty, j & 1);  // softmax has consumed S_j
-        if (j + 1 < nk) issue_s(j + 1);
-        const int n = 2 * j + 1, slot = n % kSlots;
-        mbar_wait(p_full, j & 1);
-        mbar_wait(&slot_full[slot], (n / kSlots) & 1);
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(sKV + slot * kTileBytes);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    for (int j = 0; j < nk; ++j) {
+      mbar_wait(s_empty, j & 1);  // softmax has consumed S_j
+      if (j + 1 < nk) issue_s(j + 1);
+      const int n = 2 * j + 1, slot = n % kSlots;
+      mbar_wait(p_full, j & 1);
+      mbar_wait(&slot_full[slot], (n / kSlots) & 1);
+      tc_fence_after();
+      const uint64_t dv = dKV_mn + slot * (kTileBytes >> 4);
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k) {
-          const uint64_t adesc = umma_smem_desc(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc(v_addr + k * 2048, 8192, 1024);
-          umma_f16_ss(tmO, adesc, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < kTile / 16; ++k)
+          umma_f16_ss(tmO, dP + (k >> 2) * (kTileBytes >> 4) + (k & 3) * 2, dv + k * 128, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&slot_empty[slot]);
         umma_commit(pv_done);
       }
+      __syncwarp();
     }
   } else {
-    // ------------------------------ softmax: one thread per query row ------------------------------
+    // ------------------------------ softmax: thread = (query row, 64-column half) ------------------------------
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-    float m = -INFINITY, l = 0.f;
+    const uint32_t col_base = half * 64;
+    float m = -INFINITY, l = 0.f;   // l: partial row sum over this thread's columns
     for (int j = 0; j < nk; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const bool partial = j >= g.nfull;
-      const uint32_t* mk = masks + 4 * (j - g.nfull);
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmS + lane_base + c * 32, v);
-        tmem_wait_ld();
-        const uint32_t bits = partial ? mk[c] : 0xffffffffu;
+      const uint32_t* mk = masks + 4 * (j - g.nfull) + half * 2;
+      uint32_t va[32], vb[32];
+      tmem_ld32(tmS + lane_base + col_base, va);
+      tmem_ld32(tmS + lane_base + col_base + 32, vb);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);   // scores are in registers: the MMA warp may overwrite S with Q K_{j+1}^T
+      if (partial) {
+        const uint32_t ba = mk[0], bb = mk[1];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float s = (bits >> i) & 1u ? __uint_as_float(v[i]) : -INFINITY;
-          mx = fmaxf(mx, s);
+          if (!((ba >> i) & 1u)) va[i] = 0xff800000u;   // -inf
+          if (!((bb >> i) & 1u)) vb[i] = 0xff800000u;
         }
       }
-      mx *= kLog2e;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+      float* xm = xchg + (j & 1) * 256;
+      xm[half * 128 + r] = mx;
+      pair_sync(quarter);
+      mx = fmaxf(mx, xm[(half ^ 1) * 128 + r]) * kLog2e;
       const bool need = mx > m + 8.0f;       // lazy rescale threshold (log2 units); true on the first tile
       const float m_use = need ? mx : m;
-      const float alpha = need ? exp2f(m - m_use) : 1.0f;
+      const float alpha = need ? ex2_approx(m - m_use) : 1.0f;
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);     // P buffer free, O up to tile j-1 complete
         if (__any_sync(0xffffffffu, need)) {
           tc_fence_after();
+          uint32_t v[32];
+          tmem_ld32(tmO + lane_base + half * 32, v);
+          tmem_wait_ld();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmO + lane_base + c * 32, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st32(tmO + lane_base + c * 32, v);
-          }
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st32(tmO + lane_base + half * 32, v);
           tmem_wait_st();
         }
       }
       float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmS + lane_base + c * 32, v);
-        tmem_wait_ld();
-        const uint32_t bits = partial ? mk[c] : 0xffffffffu;
-        float pr[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (bits >> i) & 1u ? __uint_as_float(v[i]) : -INFINITY;
-          pr[i] = exp2f(fmaf(s, kLog2e, -m_use));
-          sum += pr[i];
-        }
+      for (int i = 0; i < 32; ++i) {
+        const float pa = ex2_approx(fmaf(__uint_as_float(va[i]), kLog2e, -m_use));
+        const float pb = ex2_approx(fmaf(__uint_as_float(vb[i]), kLog2e, -m_use));
+        sum += pa + pb;
+        va[i] = __float_as_uint(pa);
+        vb[i] = __float_as_uint(pb);
+      }
+      const uint32_t aP = smem_u32(sP);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint4 w = make_uint4(pack_bf16x2(pr[8 * q4], pr[8 * q4 + 1]), pack_bf16x2(pr[8 * q4 + 2], pr[8 * q4 + 3]),
-                                     pack_bf16x2(pr[8 * q4 + 4], pr[8 * q4 + 5]), pack_bf16x2(pr[8 * q4 + 6], pr[8 * q4 + 7]));
-          *reinterpret_cast<uint4*>(sP + swz_off(r, c * 4 + q4)) = w;
-        }
+      for (int q4 = 0; q4 < 4; ++q4) {
+        st_shared_v4(aP + swz_off(r, half * 8 + q4),
+                     pack_bf16x2(__uint_as_float(va[8 * q4]), __uint_as_float(va[8 * q4 + 1])),
+                     pack_bf16x2(__uint_as_float(va[8 * q4 + 2]), __uint_as_float(va[8 * q4 + 3])),
+                     pack_bf16x2(__uint_as_float(va[8 * q4 + 4]), __uint_as_float(va[8 * q4 + 5])),
+                     pack_bf16x2(__uint_as_float(va[8 * q4 + 6]), __uint_as_float(va[8 * q4 + 7])));
+        st_shared_v4(aP + swz_off(r, half * 8 + 4 + q4),
+                     pack_bf16x2(__uint_as_float(vb[8 * q4]), __uint_as_float(vb[8 * q4 + 1])),
+                     pack_bf16x2(__uint_as_float(vb[8 * q4 + 2]), __uint_as_float(vb[8 * q4 + 3])),
+                     pack_bf16x2(__uint_as_float(vb[8 * q4 + 4]), __uint_as_float(vb[8 * q4 + 5])),
+                     pack_bf16x2(__uint_as_float(vb[8 * q4 + 6]), __uint_as_float(vb[8 * q4 + 7])));
       }
       l = l * alpha + sum;
       m = m_use;
       tc_fence_before();
-      mbar_arrive(s_empty);
       fence_proxy_async();   // P stores (generic proxy) -> visible to tcgen05.mma (async proxy)
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
     }
     // ------------------------------ epilogue ------------------------------
+    float* xs = xchg + (nk & 1) * 256;
+    xs[half * 128 + r] = l;
+    pair_sync(quarter);
+    l += xs[(half ^ 1) * 128 + r];
     mbar_wait(pv_done, (nk - 1) & 1);
     tc_fence_after();
     const int qv = qt * kTile + r;
@@ -212,13 +234,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
     if (qv < g.Lv) dst = p.out_v + ((long long)b * g.Lv + qv) * g.D + h * kHeadDim;
     else if (qv >= g.T0 && qv < g.T0 + g.Lt) dst = p.out_t + ((long long)b * g.Lt + (qv - g.T0)) * g.D + h * kHeadDim;
     const float inv = 1.0f / l;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t v[32];
-      tmem_ld32(tmO + lane_base + c * 32, v);
+      tmem_ld32(tmO + lane_base + half * 32, v);
       tmem_wait_ld();
       if (dst != nullptr) {
-        uint4* o = reinterpret_cast<uint4*>(dst + c * 32);
+        uint4* o = reinterpret_cast<uint4*>(dst + half * 32);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
           o[q4] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * q4]) * inv, __uint_as_float(v[8 * q4 + 1]) * inv),
@@ -227,7 +248,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
                              pack_bf16x2(__uint_as_float(v[8 * q4 + 6]) * inv, __uint_as_float(v[8 * q4 + 7]) * inv));
       }
     }
-    if (p.lse != nullptr) p.lse[((long long)b * g.H + h) * (g.ntiles * kTile) + qv] = m + log2f(l);
+    if (p.lse != nullptr && half == 0) p.lse[((long long)b * g.H + h) * (g.ntiles * kTile) + qv] = m + log2f(l);
     tc_fence_before();
   }
 

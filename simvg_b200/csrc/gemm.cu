@@ -96,7 +96,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // shfl from a fixed lane => provably warp-uniform
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
 
@@ -138,40 +138,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
-      // K-major: 8-row groups 1024 B apart; UMMA_K=16 -> +32 B.  MN-major: next 64-wide atom 8192 B
-      // away (LBO), 8 k-row groups 1024 B apart (SBO); UMMA_K=16 -> +16 rows = 2048 B.
-      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
-      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int split = t % p.k_splits;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+    // The whole warp runs this loop with warp-uniform values (descriptors stay in uniform registers); only the
+    // tcgen05.mma / tcgen05.commit instructions themselves are issued by one lane.
+    const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    // K-major: 8-row groups 1024 B apart; UMMA_K=16 -> +32 B.  MN-major: next 64-wide atom 8192 B
+    // away (LBO), 8 k-row groups 1024 B apart (SBO); UMMA_K=16 -> +16 rows = 2048 B.
+    const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+    const uint32_t a_kstep = p.a_mn ? (2048u >> 4) : (32u >> 4), b_kstep = p.b_mn ? (2048u >> 4) : (32u >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int split = t % p.k_splits;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smemA + stage * Cfg::kABytes);
-          const uint32_t b_addr = smem_u32(smemB + stage * Cfg::kBBytes);
+        const uint64_t adesc = umma_smem_desc(smem_u32(smemA + stage * Cfg::kABytes), a_lbo, 1024);
+        const uint64_t bdesc = umma_smem_desc(smem_u32(smemB + stage * Cfg::kBBytes), b_lbo, 1024);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = umma_smem_desc(a_addr + k * a_kstep, a_lbo, 1024);
-            const uint64_t bdesc = umma_smem_desc(b_addr + k * b_kstep, b_lbo, 1024);
-            umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[acc]);   // accumulator ready for the epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&acc_full[acc]);   // accumulator ready for the epilogue
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================

@@ -33,7 +33,7 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
                                             pack_bf16x2(v[6], v[7]));
 }
 
-// Sum of `val` over the W warps covering one row.  red: smem [rows_per_block][W][2 slots].
+// Sum of `val[0..N)` over the W warps covering one row group.  red: smem [rows_per_block * W * N].
 template <int N>
 __device__ __forceinline__ void row_reduce(float (&val)[N], float* red, int rg, int ww, int W, int lane) {
 #pragma unroll
@@ -53,8 +53,12 @@ __device__ __forceinline__ void row_reduce(float (&val)[N], float* red, int rg, 
   __syncthreads();
 }
 
+// Rows are processed RB at a time per row group: RB independent loads in flight per thread and one pair of block
+// barriers per RB rows instead of per row.
+constexpr int kLnMaxRB = 4;
+
 // ------------------------------------------------------------------------------------------------ LayerNorm forward
-template <typename TIn, typename TOut>
+template <typename TIn, typename TOut, int RB>
 __global__ void ln_fwd_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __restrict__ gamma,
                               const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ rstd,
                               long long R, int C, int W, int rpb, float eps) {
@@ -65,26 +69,42 @@ __global__ void ln_fwd_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, c
   float g[8], bt[8];
   load8(gamma + col, g);
   load8(beta + col, bt);
-  const long long niter = (R + (long long)gridDim.x * rpb - 1) / ((long long)gridDim.x * rpb);
+  const long long rows_per_iter = (long long)gridDim.x * rpb * RB;
+  const long long niter = (R + rows_per_iter - 1) / rows_per_iter;
   for (long long it = 0; it < niter; ++it) {
-    const long long row = (it * gridDim.x + blockIdx.x) * rpb + rg;
-    const bool ok = row < R;
-    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (ok) load8(x + row * C + col, v);
-    float s[1] = {v[0] + v[1] + v[2] + v[3] + v[4] + v[5] + v[6] + v[7]};
-    row_reduce<1>(s, red, rg, ww, W, lane);
-    const float mu = s[0] / C;
-    float q[1] = {0.f};
+    const long long row0 = ((it * gridDim.x + blockIdx.x) * rpb + rg) * RB;
+    float v[RB][8];
+    float s[RB];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { const float d = v[i] - mu; q[0] += d * d; }
-    row_reduce<1>(q, red, rg, ww, W, lane);
-    const float rs = rsqrtf(q[0] / C + eps);
-    if (ok) {
-      float o[8];
+    for (int rr = 0; rr < RB; ++rr) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (v[i] - mu) * rs * g[i] + bt[i];
-      store8(y + row * C + col, o);
-      if (ww == 0 && lane == 0) { mean[row] = mu; rstd[row] = rs; }
+      for (int i = 0; i < 8; ++i) v[rr][i] = 0.f;
+      if (row0 + rr < R) load8(x + (row0 + rr) * C + col, v[rr]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < RB; ++rr)
+      s[rr] = v[rr][0] + v[rr][1] + v[rr][2] + v[rr][3] + v[rr][4] + v[rr][5] + v[rr][6] + v[rr][7];
+    row_reduce<RB>(s, red, rg, ww, W, lane);
+    float q[RB];
+#pragma unroll
+    for (int rr = 0; rr < RB; ++rr) {
+      s[rr] /= C;
+      q[rr] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[rr][i] - s[rr]; q[rr] += d * d; }
+    }
+    row_reduce<RB>(q, red, rg, ww, W, lane);
+#pragma unroll
+    for (int rr = 0; rr < RB; ++rr) {
+      const long long row = row0 + rr;
+      if (row < R) {
+        const float rs = rsqrtf(q[rr] / C + eps);
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (v[rr][i] - s[rr]) * rs * g[i] + bt[i];
+        store8(y + row * C + col, o);
+        if (ww == 0 && lane == 0) { mean[row] = s[rr]; rstd[row] = rs; }
+      }
     }
   }
 }
@@ -122,6 +142,62 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return cdf + x * pdf;
 }
 
+// Raw (still packed) operands of one row chunk: loaded one row ahead so the global-load latency of row i+1 overlaps the
+// reduction / barriers / stores of row i.
+template <int MODE, bool DYF32>
+struct LnRaw {
+  uint4 x0, dy0;
+  uint4 x1;    // only meaningful for MODE 0 (fp32 x)
+  uint4 dy1;   // only meaningful for DYF32
+  uint4 u0;    // only meaningful for MODE 2
+  float mu, rs;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& a, const uint4& b, bool is_f32, float (&v)[8]) {
+  if (is_f32) {
+    v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+    v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+  } else {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+}
+
+template <int MODE, bool DYF32>
+__device__ __forceinline__ void ln_load_raw(const LnBwdParams& p, long long row, int col, LnRaw<MODE, DYF32>& r) {
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  r.x0 = r.dy0 = z;
+  if (MODE == 0) r.x1 = z;
+  if (DYF32) r.dy1 = z;
+  if (MODE == 2) r.u0 = z;
+  r.mu = 0.f;
+  r.rs = 0.f;
+  if (row >= p.R) return;
+  const long long off = row * p.C + col;
+  if (MODE == 0) {
+    const uint4* px = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.x) + off);
+    r.x0 = __ldg(px);
+    r.x1 = __ldg(px + 1);
+  } else {
+    r.x0 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.x) + off));
+  }
+  if (DYF32) {
+    const uint4* pd = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.dy) + off);
+    r.dy0 = __ldg(pd);
+    r.dy1 = __ldg(pd + 1);
+  } else {
+    r.dy0 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.dy) + off));
+  }
+  if (MODE == 2) r.u0 = __ldg(reinterpret_cast<const uint4*>(p.u + off));
+  r.mu = __ldg(p.mean + row);
+  r.rs = __ldg(p.rstd + row);
+}
+
+template <int MODE, bool DYF32>
 __global__ void ln_bwd_kernel(const LnBwdParams p) {
   extern __shared__ float red[];
   const int W = p.W, C = p.C, rpb = p.rpb;
@@ -131,38 +207,35 @@ __global__ void ln_bwd_kernel(const LnBwdParams p) {
   float g[8];
   load8(p.gamma + col, g);
   float acc_g[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc_b[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc_p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const long long niter = (p.R + (long long)gridDim.x * rpb - 1) / ((long long)gridDim.x * rpb);
+  const long long rows_per_iter = (long long)gridDim.x * rpb;
+  const long long niter = (p.R + rows_per_iter - 1) / rows_per_iter;
+  LnRaw<MODE, DYF32> cur, nxt;
+  ln_load_raw<MODE, DYF32>(p, (long long)blockIdx.x * rpb + rg, col, cur);
   for (long long it = 0; it < niter; ++it) {
     const long long row = (it * gridDim.x + blockIdx.x) * rpb + rg;
+    ln_load_raw<MODE, DYF32>(p, it + 1 < niter ? row + rows_per_iter : p.R, col, nxt);   // prefetch (row >= R loads nothing)
     const bool ok = row < p.R;
-    float xv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    float mu = 0.f, rs = 0.f;
-    if (ok) {
-      if (p.mode == 0) load8(reinterpret_cast<const float*>(p.x) + row * C + col, xv);
-      else load8(reinterpret_cast<const bf16*>(p.x) + row * C + col, xv);
-      if (p.dy_f32) load8(reinterpret_cast<const float*>(p.dy) + row * C + col, dy);
-      else load8(reinterpret_cast<const bf16*>(p.dy) + row * C + col, dy);
-      mu = __ldg(p.mean + row);
-      rs = __ldg(p.rstd + row);
-    }
     float xh[8], dyg[8];
+    unpack8(cur.x0, MODE == 0 ? cur.x1 : cur.x0, MODE == 0, xh);
+    unpack8(cur.dy0, DYF32 ? cur.dy1 : cur.dy0, DYF32, dyg);
+    const float rs = cur.rs;
     float s[2] = {0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      xh[i] = (xv[i] - mu) * rs;
-      dyg[i] = dy[i] * g[i];
+      xh[i] = (xh[i] - cur.mu) * rs;
+      acc_g[i] += dyg[i] * xh[i];
+      acc_b[i] += dyg[i];
+      dyg[i] *= g[i];
       s[0] += dyg[i];
       s[1] += dyg[i] * xh[i];
-      acc_g[i] += dy[i] * xh[i];
-      acc_b[i] += dy[i];
     }
     row_reduce<2>(s, red, rg, ww, W, lane);
-    const float c1 = s[0] / C, c2 = s[1] / C;
     if (ok) {
+      const float c1 = s[0] / C, c2 = s[1] / C;
       float dx[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) dx[i] = rs * (dyg[i] - c1 - xh[i] * c2);
-      if (p.mode == 0) {
+      if (MODE == 0) {
         float dr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (p.dres_in != nullptr) load8(p.dres_in + row * C + col, dr);
 #pragma unroll
@@ -174,22 +247,23 @@ __global__ void ln_bwd_kernel(const LnBwdParams p) {
           for (int i = 0; i < 8; ++i) { dr[i] *= sc; acc_p[i] += dr[i]; }
           if (p.dyb != nullptr) store8(p.dyb + row * C + col, dr);
         }
-      } else if (p.mode == 1) {
+      } else if (MODE == 1) {
         store8(p.dx + row * C + col, dx);
       } else {
         float uv[8];
-        load8(p.u + row * C + col, uv);
+        unpack8(cur.u0, cur.u0, false, uv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { dx[i] *= gelu_grad(uv[i]); acc_p[i] += dx[i]; }
         store8(p.dx + row * C + col, dx);
       }
     }
+    cur = nxt;
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     atomicAdd(p.dgamma + col + i, acc_g[i]);
     atomicAdd(p.dbeta + col + i, acc_b[i]);
-    if (p.dbias_prev != nullptr) atomicAdd(p.dbias_prev + col + i, acc_p[i]);
+    if (MODE != 1 && p.dbias_prev != nullptr) atomicAdd(p.dbias_prev + col + i, acc_p[i]);
   }
 }
 
@@ -293,10 +367,17 @@ static int ln_geometry(int C, int* W, int* rpb) {
   return 0;
 }
 
-static int ln_grid(long long R, int rpb) {
-  long long want = (R + rpb - 1) / rpb;
+static int ln_grid(long long R, int rows_per_block) {
+  long long want = (R + rows_per_block - 1) / rows_per_block;
   long long cap = (long long)sm_count() * 4;
   return (int)(want < cap ? want : cap);
+}
+// Rows batched per thread: 4 when there are plenty of rows, fewer for small problems (text tokens) so the grid stays wide.
+static int ln_rb(long long R, int rpb, int threads) {
+  // the 4-row variant of the backward kernel needs ~160 registers/thread: only legal for blocks of <= 384 threads
+  if (threads <= 384 && R >= (long long)sm_count() * 4 * rpb * 4) return 4;
+  if (R >= (long long)sm_count() * 2 * rpb * 2) return 2;
+  return 1;
 }
 
 }  // namespace simvgb
@@ -310,16 +391,22 @@ extern "C" int simvgb_ln_fwd(const void* x, int x_is_bf16, void* y, int y_is_bf1
   SIMVGB_CHECK(x && y && gamma && beta && mean && rstd, "simvgb_ln_fwd: null pointer");
   if (rows <= 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int threads = 32 * W * rpb, grid = ln_grid(rows, rpb);
-  const size_t sm = sizeof(float) * rpb * W * 2;
-  if (!x_is_bf16 && y_is_bf16)
-    ln_fwd_kernel<float, bf16><<<grid, threads, sm, s>>>((const float*)x, (bf16*)y, gamma, beta, mean, rstd, rows, C, W, rpb, eps);
-  else if (x_is_bf16 && y_is_bf16)
-    ln_fwd_kernel<bf16, bf16><<<grid, threads, sm, s>>>((const bf16*)x, (bf16*)y, gamma, beta, mean, rstd, rows, C, W, rpb, eps);
-  else if (!x_is_bf16 && !y_is_bf16)
-    ln_fwd_kernel<float, float><<<grid, threads, sm, s>>>((const float*)x, (float*)y, gamma, beta, mean, rstd, rows, C, W, rpb, eps);
-  else
-    ln_fwd_kernel<bf16, float><<<grid, threads, sm, s>>>((const bf16*)x, (float*)y, gamma, beta, mean, rstd, rows, C, W, rpb, eps);
+  const int threads = 32 * W * rpb;
+  const int rb = x_is_bf16 ? ln_rb(rows, rpb, threads) : 1;
+  const int grid = ln_grid(rows, rpb * rb);
+  const size_t sm = sizeof(float) * rpb * W * kLnMaxRB * 2;
+#define SIMVGB_LN_FWD(TI, TO, RBV) \
+  ln_fwd_kernel<TI, TO, RBV><<<grid, threads, sm, s>>>((const TI*)x, (TO*)y, gamma, beta, mean, rstd, rows, C, W, rpb, eps)
+#define SIMVGB_LN_FWD_RB(TI, TO)            \
+  do {                                      \
+    if (rb == 4) SIMVGB_LN_FWD(TI, TO, 4);  \
+    else if (rb == 2) SIMVGB_LN_FWD(TI, TO, 2); \
+    else SIMVGB_LN_FWD(TI, TO, 1);          \
+  } while (0)
+  if (!x_is_bf16 && y_is_bf16) SIMVGB_LN_FWD_RB(float, bf16);
+  else if (x_is_bf16 && y_is_bf16) SIMVGB_LN_FWD_RB(bf16, bf16);
+  else if (!x_is_bf16 && !y_is_bf16) SIMVGB_LN_FWD_RB(float, float);
+  else SIMVGB_LN_FWD_RB(bf16, float);
   SIMVGB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -333,6 +420,7 @@ extern "C" int simvgb_ln_bwd(const simvgb_ln_bwd_args* a, void* stream) {
   SIMVGB_CHECK(a->mode != 0 || a->dres_out, "simvgb_ln_bwd: mode 0 needs dres_out");
   SIMVGB_CHECK(a->mode == 0 || a->dx, "simvgb_ln_bwd: modes 1/2 need dx");
   SIMVGB_CHECK(a->mode != 2 || a->u, "simvgb_ln_bwd: mode 2 needs u");
+  SIMVGB_CHECK(a->mode == 0 || !a->dy_is_f32, "simvgb_ln_bwd: fp32 dy is only supported in mode 0");
   if (a->rows <= 0) return 0;
   LnBwdParams p;
   p.x = a->x; p.dy = a->dy; p.dy_f32 = a->dy_is_f32; p.gamma = a->gamma; p.mean = a->mean; p.rstd = a->rstd;
@@ -342,8 +430,13 @@ extern "C" int simvgb_ln_bwd(const simvgb_ln_bwd_args* a, void* stream) {
   p.dbias_prev = a->dbias_prev; p.dx = reinterpret_cast<bf16*>(a->dx); p.u = reinterpret_cast<const bf16*>(a->u);
   p.R = a->rows; p.C = a->C; p.W = W; p.rpb = rpb; p.mode = a->mode;
   const int threads = 32 * W * rpb;
-  int grid = ln_grid(a->rows, rpb);
-  ln_bwd_kernel<<<grid, threads, sizeof(float) * rpb * W * 2, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  const int grid = ln_grid(a->rows, rpb);
+  const size_t sm = sizeof(float) * rpb * W * kLnMaxRB * 2;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p.mode == 0 && p.dy_f32) ln_bwd_kernel<0, true><<<grid, threads, sm, st>>>(p);
+  else if (p.mode == 0) ln_bwd_kernel<0, false><<<grid, threads, sm, st>>>(p);
+  else if (p.mode == 1) ln_bwd_kernel<1, false><<<grid, threads, sm, st>>>(p);
+  else ln_bwd_kernel<2, false><<<grid, threads, sm, st>>>(p);
   SIMVGB_CUDA(cudaGetLastError());
   return 0;
 }
