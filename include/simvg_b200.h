@@ -105,14 +105,16 @@ int simvgb_attn_bwd(const simvgb_attn_args* args, void* stream);
  * ffn_layernorm / encoder.layer_norm (beit3_base.py:41,86,136,157,228,396-397; torchscale A.4, A.5) — the
  * caller launches once per expert (vision rows with the A parameters, text rows with the B parameters).
  * ------------------------------------------------------------------------------------------------ */
+/* act = 1: y = LN(gelu_erf(x)) — the FFN's activation (F.gelu(x.float()), A.5) fused in front of ffn_layernorm. */
 int simvgb_ln_fwd(const void* x, int x_is_bf16, void* y, int y_is_bf16, const float* gamma, const float* beta,
-                  float* mean, float* rstd, int64_t rows, int C, float eps, void* stream);
+                  float* mean, float* rstd, int64_t rows, int C, float eps, int act, void* stream);
 
 /* Backward.  mode 0: residual-stream LN — dres_out = dres_in + LN'(dy), optionally also emits
  *   dyb = bf16(row_scale * dres_out) (the dY operand of the preceding out_proj / fc2 GEMMs) and
  *   dbias_prev += colsum(row_scale * dres_out) (their bias gradient).           (beit3_base.py:123-124,146-169)
  * mode 1: inner attention LN — dx(bf16) = LN'(dy).
- * mode 2: FFN LN fused with GELU backward — dx(bf16) = LN'(dy) * gelu'(u), dbias_prev += colsum(dx) (fc1 bias). */
+ * mode 2: FFN LN fused with GELU backward — the LN input was gelu(u) and is recomputed from u (x is ignored, may be
+ *   NULL): dx(bf16) = LN'(dy) * gelu'(u), dbias_prev += colsum(dx) (fc1 bias). */
 typedef struct simvgb_ln_bwd_args {
   int32_t mode, C;
   int64_t rows;

@@ -50,9 +50,7 @@ struct GemmParams {
   int accumulate;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
+__device__ __forceinline__ float gelu_erf(float x) { return gelu_fwd(x); }
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)

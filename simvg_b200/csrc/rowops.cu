@@ -58,7 +58,7 @@ __device__ __forceinline__ void row_reduce(float (&val)[N], float* red, int rg, 
 constexpr int kLnMaxRB = 4;
 
 // ------------------------------------------------------------------------------------------------ LayerNorm forward
-template <typename TIn, typename TOut, int RB>
+template <typename TIn, typename TOut, int RB, bool GELU>
 __global__ void ln_fwd_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __restrict__ gamma,
                               const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ rstd,
                               long long R, int C, int W, int rpb, float eps) {
@@ -79,7 +79,13 @@ __global__ void ln_fwd_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, c
     for (int rr = 0; rr < RB; ++rr) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[rr][i] = 0.f;
-      if (row0 + rr < R) load8(x + (row0 + rr) * C + col, v[rr]);
+      if (row0 + rr < R) {
+        load8(x + (row0 + rr) * C + col, v[rr]);
+        if (GELU) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[rr][i] = gelu_fwd(v[rr][i]);
+        }
+      }
     }
 #pragma unroll
     for (int rr = 0; rr < RB; ++rr)
@@ -114,7 +120,8 @@ __global__ void ln_fwd_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, c
 //                              dbias_prev += colsum(row_scale * dres_out)  (out_proj / fc2 bias gradient of the sub-layer
 //                              whose output joined the stream at this point)
 // mode 1 (inner attention LN): dx (bf16) = LN'(dy)
-// mode 2 (FFN LN + GELU):      du (bf16) = LN'(dy) * gelu'(u);  dbias_prev += colsum(du)  (fc1 bias gradient)
+// mode 2 (FFN LN + GELU):      the LN input was gelu(u) (recomputed here from u, never stored);
+//                              du (bf16) = LN'(dy) * gelu'(u);  dbias_prev += colsum(du)  (fc1 bias gradient)
 struct LnBwdParams {
   const void* x;         // LN input: fp32 (mode 0) / bf16 (modes 1,2)
   const void* dy;        // bf16, or fp32 when dy_f32
@@ -135,12 +142,6 @@ struct LnBwdParams {
   long long R;
   int C, W, rpb, mode;
 };
-
-__device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
-}
 
 // Raw (still packed) operands of one row chunk: loaded one row ahead so the global-load latency of row i+1 overlaps the
 // reduction / barriers / stores of row i.
@@ -182,9 +183,9 @@ __device__ __forceinline__ void ln_load_raw(const LnBwdParams& p, long long row,
     const uint4* px = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.x) + off);
     r.x0 = __ldg(px);
     r.x1 = __ldg(px + 1);
-  } else {
+  } else if (MODE == 1) {
     r.x0 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.x) + off));
-  }
+  }   // MODE 2: the LN input is gelu(u), recomputed from u
   if (DYF32) {
     const uint4* pd = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.dy) + off);
     r.dy0 = __ldg(pd);
@@ -215,8 +216,14 @@ __global__ void ln_bwd_kernel(const LnBwdParams p) {
     const long long row = (it * gridDim.x + blockIdx.x) * rpb + rg;
     ln_load_raw<MODE, DYF32>(p, it + 1 < niter ? row + rows_per_iter : p.R, col, nxt);   // prefetch (row >= R loads nothing)
     const bool ok = row < p.R;
-    float xh[8], dyg[8];
-    unpack8(cur.x0, MODE == 0 ? cur.x1 : cur.x0, MODE == 0, xh);
+    float xh[8], dyg[8], gg[8];   // gg: gelu'(u) (MODE 2)
+    if (MODE == 2) {
+      unpack8(cur.u0, cur.u0, false, xh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { float gv; gg[i] = gelu_fwd_grad(xh[i], gv); xh[i] = gv; }
+    } else {
+      unpack8(cur.x0, MODE == 0 ? cur.x1 : cur.x0, MODE == 0, xh);
+    }
     unpack8(cur.dy0, DYF32 ? cur.dy1 : cur.dy0, DYF32, dyg);
     const float rs = cur.rs;
     float s[2] = {0.f, 0.f};
@@ -250,10 +257,8 @@ __global__ void ln_bwd_kernel(const LnBwdParams p) {
       } else if (MODE == 1) {
         store8(p.dx + row * C + col, dx);
       } else {
-        float uv[8];
-        unpack8(cur.u0, cur.u0, false, uv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { dx[i] *= gelu_grad(uv[i]); acc_p[i] += dx[i]; }
+        for (int i = 0; i < 8; ++i) { dx[i] *= gg[i]; acc_p[i] += dx[i]; }
         store8(p.dx + row * C + col, dx);
       }
     }
@@ -277,13 +282,24 @@ __global__ void colsum_kernel(const TIn* __restrict__ in, float* __restrict__ ou
   const int col = (blockIdx.x * 32 + cx) * 8;
   if (col >= C) return;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long row = (long long)blockIdx.y * 8 + ry; row < R; row += (long long)gridDim.y * 8) {
-    float v[8];
-    load8(in + row * ld + col, v);
-    const float sc = row_scale != nullptr ? __ldg(row_scale + row / rows_per_scale) : 1.0f;
+  const long long stride = (long long)gridDim.y * 8;
+  for (long long row = (long long)blockIdx.y * 8 + ry; row < R; row += 4 * stride) {
+    float v[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { v[i] *= sc; acc[i] += v[i]; }
-    if (ob != nullptr) store8(ob + row * C + col, v);
+    for (int k = 0; k < 4; ++k) {     // 4 independent loads in flight per thread
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[k][i] = 0.f;
+      if (row + k * stride < R) load8(in + (row + k * stride) * ld + col, v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long rk = row + k * stride;
+      if (rk >= R) break;
+      const float sc = row_scale != nullptr ? __ldg(row_scale + rk / rows_per_scale) : 1.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[k][i] *= sc; acc[i] += v[k][i]; }
+      if (ob != nullptr) store8(ob + rk * C + col, v[k]);
+    }
   }
   if (out != nullptr) {
 #pragma unroll
@@ -385,7 +401,7 @@ static int ln_rb(long long R, int rpb, int threads) {
 using namespace simvgb;
 
 extern "C" int simvgb_ln_fwd(const void* x, int x_is_bf16, void* y, int y_is_bf16, const float* gamma, const float* beta,
-                             float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
+                             float* mean, float* rstd, int64_t rows, int C, float eps, int act, void* stream) {
   int W, rpb;
   SIMVGB_CHECK(ln_geometry(C, &W, &rpb) == 0, "simvgb_ln_fwd: C=%d must be a multiple of 256 and <= 8192", C);
   SIMVGB_CHECK(x && y && gamma && beta && mean && rstd, "simvgb_ln_fwd: null pointer");
@@ -395,8 +411,11 @@ extern "C" int simvgb_ln_fwd(const void* x, int x_is_bf16, void* y, int y_is_bf1
   const int rb = x_is_bf16 ? ln_rb(rows, rpb, threads) : 1;
   const int grid = ln_grid(rows, rpb * rb);
   const size_t sm = sizeof(float) * rpb * W * kLnMaxRB * 2;
-#define SIMVGB_LN_FWD(TI, TO, RBV) \
-  ln_fwd_kernel<TI, TO, RBV><<<grid, threads, sm, s>>>((const TI*)x, (TO*)y, gamma, beta, mean, rstd, rows, C, W, rpb, eps)
+#define SIMVGB_LN_FWD(TI, TO, RBV)                                                                                        \
+  do {                                                                                                                  \
+    if (act) ln_fwd_kernel<TI, TO, RBV, true><<<grid, threads, sm, s>>>((const TI*)x, (TO*)y, gamma, beta, mean, rstd, rows, C, W, rpb, eps); \
+    else ln_fwd_kernel<TI, TO, RBV, false><<<grid, threads, sm, s>>>((const TI*)x, (TO*)y, gamma, beta, mean, rstd, rows, C, W, rpb, eps);   \
+  } while (0)
 #define SIMVGB_LN_FWD_RB(TI, TO)            \
   do {                                      \
     if (rb == 4) SIMVGB_LN_FWD(TI, TO, 4);  \
@@ -416,7 +435,7 @@ extern "C" int simvgb_ln_bwd(const simvgb_ln_bwd_args* a, void* stream) {
   int W, rpb;
   SIMVGB_CHECK(ln_geometry(a->C, &W, &rpb) == 0, "simvgb_ln_bwd: C=%d must be a multiple of 256 and <= 8192", a->C);
   SIMVGB_CHECK(a->mode >= 0 && a->mode <= 2, "simvgb_ln_bwd: bad mode %d", a->mode);
-  SIMVGB_CHECK(a->x && a->dy && a->gamma && a->mean && a->rstd && a->dgamma && a->dbeta, "simvgb_ln_bwd: null pointer");
+  SIMVGB_CHECK((a->x || a->mode == 2) && a->dy && a->gamma && a->mean && a->rstd && a->dgamma && a->dbeta, "simvgb_ln_bwd: null pointer");
   SIMVGB_CHECK(a->mode != 0 || a->dres_out, "simvgb_ln_bwd: mode 0 needs dres_out");
   SIMVGB_CHECK(a->mode == 0 || a->dx, "simvgb_ln_bwd: modes 1/2 need dx");
   SIMVGB_CHECK(a->mode != 2 || a->u, "simvgb_ln_bwd: mode 2 needs u");

@@ -92,7 +92,7 @@ def _lib_setup():
     if not getattr(lib, "_simvgb_typed", False):
         lib.simvgb_attn_lse_stride.restype = L.c_int
         lib.simvgb_ln_fwd.argtypes = [L.c_vp, L.c_int, L.c_vp, L.c_int, L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_i64, L.c_int,
-                                      L.c_f32, L.c_vp]
+                                      L.c_f32, L.c_int, L.c_vp]
         lib.simvgb_colsum.argtypes = [L.c_vp, L.c_int, L.c_vp, L.c_vp, L.c_vp, L.c_int, L.c_i64, L.c_int, L.c_i64, L.c_vp]
         lib.simvgb_cast_bf16.argtypes = [L.c_vp, L.c_vp, L.c_i64, L.c_vp]
         lib.simvgb_im2col_patch.argtypes = [L.c_vp, L.c_vp, L.c_int, L.c_int, L.c_int, L.c_vp]
@@ -219,7 +219,7 @@ def attn_bwd(qkv_v, qkv_t, pad, out_v, out_t, lse, dout_v, dout_t, B, H, Lv, Lt,
 
 
 # ---------------------------------------------------------------------------------------------- row kernels
-def ln_fwd(x, gamma, beta, eps, out_dtype=bf16):
+def ln_fwd(x, gamma, beta, eps, out_dtype=bf16, gelu=False):
     L.require_device(x)
     lib = _lib_setup()
     R, C = x.shape
@@ -227,7 +227,7 @@ def ln_fwd(x, gamma, beta, eps, out_dtype=bf16):
     mean = torch.empty(R, device=x.device, dtype=f32)
     rstd = torch.empty(R, device=x.device, dtype=f32)
     L.check(lib.simvgb_ln_fwd(x.data_ptr(), int(x.dtype == bf16), y.data_ptr(), int(out_dtype == bf16), gamma.data_ptr(),
-                              beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), R, C, eps, _stream()), "ln_fwd")
+                              beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), R, C, eps, int(gelu), _stream()), "ln_fwd")
     _launches[0] += 1
     return y, mean, rstd
 
@@ -235,10 +235,10 @@ def ln_fwd(x, gamma, beta, eps, out_dtype=bf16):
 def ln_bwd(mode, x, dy, gamma, mean, rstd, dgamma, dbeta, *, dres_in=None, dres_out=None, dyb=None, row_scale=None,
            rows_per_scale=1, dbias_prev=None, dx=None, u=None):
     lib = _lib_setup()
-    R, C = x.shape
+    R, C = dy.shape
     a = LnBwdArgs()
     a.mode, a.C, a.rows = mode, C, R
-    a.x, a.dy, a.dy_is_f32 = x.data_ptr(), dy.data_ptr(), int(dy.dtype == f32)
+    a.x, a.dy, a.dy_is_f32 = _p(x), dy.data_ptr(), int(dy.dtype == f32)
     a.gamma, a.mean, a.rstd = gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr()
     a.dgamma, a.dbeta = dgamma.data_ptr(), dbeta.data_ptr()
     a.dres_in, a.dres_out, a.dyb = _p(dres_in), _p(dres_out), _p(dyb)

@@ -330,14 +330,12 @@ def encoder_forward(mod, image, ids, pad_mask, save):
             xmid = K.gemm(a, G.wb["o_w"], Rs[g], D, D, epilogue=K.EPI_RESID, bias=G.w["o_b"], res=x[g], row_scale=dp1,
                           rows_per_scale=Ls[g])
             h2, m2, r2 = K.ln_fwd(xmid, G.w["ln2_w"], G.w["ln2_b"], eps)
-            u = torch.empty(Rs[g], F, device=image.device, dtype=bf16)
-            gl = torch.empty(Rs[g], F, device=image.device, dtype=bf16)
-            K.gemm(h2, G.wb["fc1_w"], Rs[g], F, D, epilogue=K.EPI_GELU, bias=G.w["fc1_b"], out=u, out2=gl)
-            f, mf, rf = K.ln_fwd(gl, G.w["fl_w"], G.w["fl_b"], eps)
+            u = K.gemm(h2, G.wb["fc1_w"], Rs[g], F, D, epilogue=K.EPI_BF16, bias=G.w["fc1_b"])
+            f, mf, rf = K.ln_fwd(u, G.w["fl_w"], G.w["fl_b"], eps, gelu=True)   # LN_F(gelu(u)): the activation is never stored
             xn = K.gemm(f, G.wb["fc2_w"], Rs[g], D, F, epilogue=K.EPI_RESID, bias=G.w["fc2_b"], res=xmid, row_scale=dp2,
                         rows_per_scale=Ls[g])
             if save:
-                sv[g].update(o=o[g], a=a, mi=mi, ri=ri, xmid=xmid, h2=h2, m2=m2, r2=r2, u=u, gl=gl, f=f, mf=mf, rf=rf)
+                sv[g].update(o=o[g], a=a, mi=mi, ri=ri, xmid=xmid, h2=h2, m2=m2, r2=r2, u=u, f=f, mf=mf, rf=rf)
             x[g] = xn
         if save:
             saved.append(dict(g=sv, lse=lse, dp=(dp1, dp2)))
@@ -387,7 +385,7 @@ def encoder_backward(mod, ctx, dxv, dxt):
             K.wgrad(dyb[g], sv["f"], D, F, R, out=G.g["fc2_w"])
             df = K.gemm(dyb[g], G.wb["fc2_w"], R, F, D, b_mn=True, epilogue=K.EPI_BF16)
             du = torch.empty(R, F, device=dev, dtype=bf16)
-            K.ln_bwd(2, sv["gl"], df, G.w["fl_w"], sv["mf"], sv["rf"], G.g["fl_w"], G.g["fl_b"], dx=du, u=sv["u"],
+            K.ln_bwd(2, None, df, G.w["fl_w"], sv["mf"], sv["rf"], G.g["fl_w"], G.g["fl_b"], dx=du, u=sv["u"],
                      dbias_prev=G.g["fc1_b"])
             del df
             K.wgrad(du, sv["h2"], F, D, R, out=G.g["fc1_w"])

@@ -214,11 +214,16 @@ def test_layernorm_bwd_inner_and_gelu_modes(K, C):
     dx_ref, dg_ref, db_ref = _ln_ref_bwd(gl, dy, g)
     assert maxrel(dx, dx_ref) < 4e-3 and maxrel(dg, dg_ref) < 1e-4 and maxrel(db, db_ref) < 1e-4
     dg.zero_(); db.zero_()
-    du = torch.empty(R, C, device=DEV, dtype=torch.bfloat16)
-    K.ln_bwd(2, gl, dy, g, mean, rstd, dg, db, dx=du, u=u, dbias_prev=dbias)
+    # mode 2: the LN input is gelu(u), recomputed in-kernel from u (never stored); fused forward = LN(gelu(u))
+    yf, mean2, rstd2 = K.ln_fwd(u, g, torch.zeros_like(g), 1e-5, out_dtype=torch.float32, gelu=True)
     uf = u.float().requires_grad_(True)
-    torch.nn.functional.gelu(uf).backward(dx_ref)
-    assert maxrel(du, uf.grad) < 4e-3 and maxrel(dbias, uf.grad.sum(0)) < 5e-3
+    gg = g.clone().requires_grad_(True)
+    y_ref = torch.nn.functional.layer_norm(torch.nn.functional.gelu(uf), (C,), gg, torch.zeros_like(g), 1e-5)
+    assert maxrel(yf, y_ref) < 1e-5
+    y_ref.backward(dy.float())
+    du = torch.empty(R, C, device=DEV, dtype=torch.bfloat16)
+    K.ln_bwd(2, None, dy, g, mean2, rstd2, dg, db, dx=du, u=u, dbias_prev=dbias)
+    assert maxrel(du, uf.grad) < 4e-3 and maxrel(dbias, uf.grad.sum(0)) < 5e-3 and maxrel(dg, gg.grad) < 1e-4
 
 
 def test_colsum_cast_embed_im2col(K):
