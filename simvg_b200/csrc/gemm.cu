@@ -204,16 +204,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         const bool full_chunk = (col0 + 32 <= p.N) && ((p.ldo & 7) == 0);
         if (p.bias != nullptr && p.epilogue != SIMVGB_EPI_ATOMIC) {
+          if (col0 + 32 <= p.N) {   // 8 vector loads (all lanes read the same addresses: one broadcast transaction each)
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(b4 + j);
+              f[4 * j] += bv.x; f[4 * j + 1] += bv.y; f[4 * j + 2] += bv.z; f[4 * j + 3] += bv.w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+          }
         }
         const long long off = (long long)row * p.ldo + col0;
         switch (p.epilogue) {
           case SIMVGB_EPI_BF16: {
+            if (col0 + 32 <= p.scale_cols) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.scale_cols) f[j] *= p.scale;
+              for (int j = 0; j < 32; ++j) f[j] *= p.scale;
+            } else if (col0 < p.scale_cols) {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.scale_cols) f[j] *= p.scale;
+            }
             if (full_chunk) {
               uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + off);
 #pragma unroll
@@ -280,8 +292,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           } break;
           default: {  // SIMVGB_EPI_ATOMIC
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) atomicAdd(p.out_f32 + off + j, f[j]);
+            if (full_chunk) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out_f32 + off + 4 * j), "f"(f[4 * j]),
+                             "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                             : "memory");
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(p.out_f32 + off + j, f[j]);
+            }
           } break;
         }
       }
@@ -363,6 +383,7 @@ extern "C" int simvgb_gemm(const simvgb_gemm_args* a, void* stream) {
   SIMVGB_CHECK(a->A && a->B, "simvgb_gemm: null operand");
   SIMVGB_CHECK((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
                "simvgb_gemm: operands must be 16-byte aligned");
+  SIMVGB_CHECK(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "simvgb_gemm: bias must be 16-byte aligned");
   SIMVGB_CHECK((a->lda % 8) == 0 && (a->ldb % 8) == 0, "simvgb_gemm: lda/ldb must be multiples of 8 (TMA 16-byte strides)");
   SIMVGB_CHECK(a->epilogue >= 0 && a->epilogue <= SIMVGB_EPI_ATOMIC, "simvgb_gemm: bad epilogue %d", a->epilogue);
   SIMVGB_CHECK(a->k_splits <= 1 || a->epilogue == SIMVGB_EPI_ATOMIC, "simvgb_gemm: k_splits > 1 needs the atomic epilogue");

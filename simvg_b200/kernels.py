@@ -19,6 +19,7 @@ _launches = [0]
 
 # Optional per-family device timing (bench.py's roofline leg): family -> list of (start event, end event, flops).
 _prof = [None]
+_prof_detail = [False]   # per-shape GEMM families (tools/gemm_shapes.py)
 
 
 def profile_start():
@@ -143,26 +144,29 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, bias=None,
     a.row_scale = _p(row_scale)
     a.rows_per_scale = rows_per_scale
     a.accumulate = int(accumulate)
-    with _timed("gemm", 2.0 * M * N * K):
+    fam = "gemm" if not _prof_detail[0] else "gemm M=%d N=%d K=%d a_mn=%d b_mn=%d epi=%d ks=%d" % (M, N, K, a_mn, b_mn, epilogue, k_splits)
+    with _timed(fam, 2.0 * M * N * K):
         L.check(lib.simvgb_gemm(ctypes.byref(a), L.c_vp(_stream())), "gemm")
     _launches[0] += 1
     return out
 
 
 def wgrad_splits(M, N, K):
-    """Split-K factor for a weight-gradient GEMM (few output tiles, very long K)."""
+    """Split-K factor for a weight-gradient GEMM (few output tiles, very long K).  Every split pays a full fp32 atomic
+    epilogue for its 128 x 256 tile, so a split must own at least 32 k-blocks (2048 rows) to amortise it."""
     tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
     kb = (K + 63) // 64
-    ks = max(1, min((2 * 148 + tiles - 1) // tiles, kb // 4 if kb >= 8 else 1))
-    return ks
+    return max(1, min((2 * 148 + tiles - 1) // tiles, kb // 32))
 
 
 def wgrad(dY, X, Dout, Din, R, out=None):
     """dW[Dout, Din] (+)= dY[R, Dout]^T @ X[R, Din]; both operands read MN-major, fp32 atomics over split-K."""
     if out is None:
         out = torch.zeros(Dout, Din, device=dY.device, dtype=f32)
-    return gemm(dY, X, Dout, Din, R, a_mn=True, b_mn=True, epilogue=EPI_ATOMIC, out=out,
-                k_splits=wgrad_splits(Dout, Din, R))
+    ks = wgrad_splits(Dout, Din, R)
+    if ks == 1:   # no split: plain read-modify-write accumulate, no atomics
+        return gemm(dY, X, Dout, Din, R, a_mn=True, b_mn=True, epilogue=EPI_F32, out=out, accumulate=True)
+    return gemm(dY, X, Dout, Din, R, a_mn=True, b_mn=True, epilogue=EPI_ATOMIC, out=out, k_splits=ks)
 
 
 # ---------------------------------------------------------------------------------------------- attention
