@@ -341,8 +341,8 @@ def run_ours(args, cfg_name):
                 "last_loss": last_loss},
         "gpu_launches": launches,
         "step_gflops_per_image": gf,
-        "step_tflops": ips * gf / 1e3,
-        "step_frac_of_peak": ips * gf / 1e3 / peak_tf,
+        "step_tflops": ips * gf / 1e3,   # whole job
+        "step_frac_of_peak": ips * gf / 1e3 / peak_tf / world,
         "roofline": roofline,
         "cpu_baseline": cpu,
     }

@@ -417,9 +417,9 @@ extern "C" int simvgb_attn_bwd(const simvgb_attn_args* a, void* stream) {
   p.dq_acc_v = a->dq_acc_v;
   p.dq_acc_t = a->dq_acc_t;
   {
-    const char* e = getenv("SIMVGB_ATTN_DEBUG");
-    p.dbg = e ? atoi(e) : 0;
-    p.ts = g_attn_trace;
+    static const int dbg_env = [] { const char* e = getenv("SIMVGB_ATTN_DEBUG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg_env;          // timing ablations for tools/attn_ablate.py; 0 in production
+    p.ts = g_attn_trace;      // optional clock64 trace (tools/attn_trace.py)
   }
   const int lse_stride = p.g.ntiles * kTile;
   AttnMaps6 maps;

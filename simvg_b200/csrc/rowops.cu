@@ -115,6 +115,75 @@ __global__ void ln_fwd_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, c
   }
 }
 
+// Warp-per-row forward: a warp owns a whole row (NCH chunks of 8 columns per lane), issues all its loads up front, keeps
+// the fp32 values in registers and reduces with shuffles only — no shared memory, no block barriers, rows independent.
+template <typename TIn, typename TOut, int NCH, bool GELU>
+__global__ void __launch_bounds__(128) ln_fwd_warp_kernel(const TIn* __restrict__ x, TOut* __restrict__ y,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ mean, float* __restrict__ rstd, long long R,
+                                                          float eps) {
+  constexpr int C = NCH * 256;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * 4;
+  for (long long row = warp0; row < R; row += nwarps) {
+    float v[NCH][8];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) load8(x + row * C + (c * 32 + lane) * 8, v[c]);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (GELU) v[c][i] = gelu_fwd(v[c][i]);
+        s += v[c][i];
+      }
+    }
+    const float mu = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[c][i] - mu; q += d * d; }
+    }
+    const float rs = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      float g[8], bt[8], o[8];
+      load8(gamma + col, g);
+      load8(beta + col, bt);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (v[c][i] - mu) * rs * g[i] + bt[i];
+      store8(y + row * C + col, o);
+    }
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  }
+}
+
+template <typename TIn, typename TOut, int NCH>
+static void launch_ln_fwd_warp(const void* x, void* y, const float* gamma, const float* beta, float* mean, float* rstd,
+                               long long R, float eps, int act, cudaStream_t s) {
+  long long blocks = (R + 3) / 4;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (act) ln_fwd_warp_kernel<TIn, TOut, NCH, true><<<(unsigned)blocks, 128, 0, s>>>((const TIn*)x, (TOut*)y, gamma, beta, mean, rstd, R, eps);
+  else ln_fwd_warp_kernel<TIn, TOut, NCH, false><<<(unsigned)blocks, 128, 0, s>>>((const TIn*)x, (TOut*)y, gamma, beta, mean, rstd, R, eps);
+}
+
+template <typename TIn, typename TOut>
+static bool dispatch_ln_fwd_warp(int C, const void* x, void* y, const float* gamma, const float* beta, float* mean,
+                                 float* rstd, long long R, float eps, int act, cudaStream_t s) {
+  switch (C) {
+    case 256: launch_ln_fwd_warp<TIn, TOut, 1>(x, y, gamma, beta, mean, rstd, R, eps, act, s); return true;
+    case 768: launch_ln_fwd_warp<TIn, TOut, 3>(x, y, gamma, beta, mean, rstd, R, eps, act, s); return true;
+    case 1024: launch_ln_fwd_warp<TIn, TOut, 4>(x, y, gamma, beta, mean, rstd, R, eps, act, s); return true;
+    case 3072: launch_ln_fwd_warp<TIn, TOut, 12>(x, y, gamma, beta, mean, rstd, R, eps, act, s); return true;
+    case 4096: launch_ln_fwd_warp<TIn, TOut, 16>(x, y, gamma, beta, mean, rstd, R, eps, act, s); return true;
+    default: return false;   // other widths: generic multi-warp-per-row kernel below
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
 // mode 0 (residual-stream LN): dres_out = dres_in + LN'(dy);  optional dyb = bf16(row_scale * dres_out) and
 //                              dbias_prev += colsum(row_scale * dres_out)  (out_proj / fc2 bias gradient of the sub-layer
@@ -407,6 +476,17 @@ extern "C" int simvgb_ln_fwd(const void* x, int x_is_bf16, void* y, int y_is_bf1
   SIMVGB_CHECK(x && y && gamma && beta && mean && rstd, "simvgb_ln_fwd: null pointer");
   if (rows <= 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  {
+    bool done;
+    if (!x_is_bf16 && y_is_bf16) done = dispatch_ln_fwd_warp<float, bf16>(C, x, y, gamma, beta, mean, rstd, rows, eps, act, s);
+    else if (x_is_bf16 && y_is_bf16) done = dispatch_ln_fwd_warp<bf16, bf16>(C, x, y, gamma, beta, mean, rstd, rows, eps, act, s);
+    else if (!x_is_bf16 && !y_is_bf16) done = dispatch_ln_fwd_warp<float, float>(C, x, y, gamma, beta, mean, rstd, rows, eps, act, s);
+    else done = dispatch_ln_fwd_warp<bf16, float>(C, x, y, gamma, beta, mean, rstd, rows, eps, act, s);
+    if (done) {
+      SIMVGB_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   const int threads = 32 * W * rpb;
   const int rb = x_is_bf16 ? ln_rb(rows, rpb, threads) : 1;
   const int grid = ln_grid(rows, rpb * rb);

@@ -21,7 +21,11 @@ for C in (768, 3072):
     _,mean,rstd=K.ln_fwd(x32,g,b,1e-5)
     dg=torch.zeros(C,device=dev); db=torch.zeros(C,device=dev); dbp=torch.zeros(C,device=dev)
     dres=torch.randn(R,C,device=dev); dyb=torch.empty(R,C,device=dev,dtype=torch.bfloat16); dx=torch.empty(R,C,device=dev,dtype=torch.bfloat16)
-    out.append('C=%d fwd f32->bf16 %.3f  fwd bf16->bf16 %.3f' % (C, t(lambda: K.ln_fwd(x32,g,b,1e-5)), t(lambda: K.ln_fwd(xb,g,b,1e-5))))
+    try:
+        tg = t(lambda: K.ln_fwd(xb,g,b,1e-5,gelu=True))
+    except TypeError:
+        tg = float('nan')
+    out.append('C=%d fwd f32->bf16 %.3f  fwd bf16->bf16 %.3f  +gelu %.3f' % (C, t(lambda: K.ln_fwd(x32,g,b,1e-5)), t(lambda: K.ln_fwd(xb,g,b,1e-5)), tg))
     out.append('C=%d bwd mode0 %.3f  mode1 %.3f  mode2 %.3f' % (C,
         t(lambda: K.ln_bwd(0,x32,dy,g,mean,rstd,dg,db,dres_in=dres,dres_out=dres,dyb=dyb,dbias_prev=dbp)),
         t(lambda: K.ln_bwd(1,xb,dy,g,mean,rstd,dg,db,dx=dx)),

@@ -31,10 +31,12 @@ def main():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    if os.environ.get("NOPROF"):
-        for _ in range(int(os.environ.get("STEPS", 2))):
+    if os.environ.get("NOPROF"):   # under ncu: `--profile-from-start off` captures only these steps
+        torch.cuda.cudart().cudaProfilerStart()
+        for _ in range(int(os.environ.get("STEPS", 1))):
             step()
         torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
         return
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
