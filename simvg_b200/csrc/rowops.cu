@@ -267,8 +267,8 @@ __device__ __forceinline__ void ln_load_raw(const LnBwdParams& p, long long row,
   r.rs = __ldg(p.rstd + row);
 }
 
-template <int MODE, bool DYF32>
-__global__ void ln_bwd_kernel(const LnBwdParams p) {
+template <int MODE, bool DYF32, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) ln_bwd_kernel(const LnBwdParams p) {
   extern __shared__ float red[];
   const int W = p.W, C = p.C, rpb = p.rpb;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -338,6 +338,195 @@ __global__ void ln_bwd_kernel(const LnBwdParams p) {
     atomicAdd(p.dgamma + col + i, acc_g[i]);
     atomicAdd(p.dbeta + col + i, acc_b[i]);
     if (MODE != 1 && p.dbias_prev != nullptr) atomicAdd(p.dbias_prev + col + i, acc_p[i]);
+  }
+}
+
+// Warp-per-row backward for narrow rows (C <= 1024, i.e. the residual-stream and inner-attention LayerNorms): a warp owns
+// whole rows, all loads of a row are in flight at once, row reductions are shuffles only, column accumulators live in
+// registers and are combined across the block's 4 warps through shared memory before one atomic per column per block.
+template <int MODE, bool DYF32, int NCH>
+__global__ void __launch_bounds__(128) ln_bwd_warp_kernel(const LnBwdParams p) {
+  constexpr int C = NCH * 256;
+  __shared__ float sacc[3][C];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 3 * C; i += 128) (&sacc[0][0])[i] = 0.f;
+  __syncthreads();
+  float g[NCH][8], acc_g[NCH][8], acc_b[NCH][8], acc_p[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    load8(p.gamma + (c * 32 + lane) * 8, g[c]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc_g[c][i] = 0.f; acc_b[c][i] = 0.f; acc_p[c][i] = 0.f; }
+  }
+  const bool want_p = MODE == 0 && (p.dyb != nullptr || p.dbias_prev != nullptr);
+  const long long nwarps = (long long)gridDim.x * 4;
+  for (long long row = (long long)blockIdx.x * 4 + warp; row < p.R; row += nwarps) {
+    float xh[NCH][8], dyg[NCH][8], dr[NCH][8];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const long long off = row * C + (c * 32 + lane) * 8;
+      if (MODE == 0) load8(reinterpret_cast<const float*>(p.x) + off, xh[c]);
+      else load8(reinterpret_cast<const bf16*>(p.x) + off, xh[c]);
+      if (DYF32) load8(reinterpret_cast<const float*>(p.dy) + off, dyg[c]);
+      else load8(reinterpret_cast<const bf16*>(p.dy) + off, dyg[c]);
+      if (MODE == 0) {
+        if (p.dres_in != nullptr) load8(p.dres_in + off, dr[c]);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dr[c][i] = 0.f;
+        }
+      }
+    }
+    const float mu = __ldg(p.mean + row), rs = __ldg(p.rstd + row);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xh[c][i] = (xh[c][i] - mu) * rs;
+        acc_g[c][i] += dyg[c][i] * xh[c][i];
+        acc_b[c][i] += dyg[c][i];
+        dyg[c][i] *= g[c][i];
+        s1 += dyg[c][i];
+        s2 += dyg[c][i] * xh[c][i];
+      }
+    }
+    const float c1 = warp_sum(s1) * (1.0f / C), c2 = warp_sum(s2) * (1.0f / C);
+    const float sc = (want_p && p.row_scale != nullptr) ? __ldg(p.row_scale + row / p.rows_per_scale) : 1.0f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const long long off = row * C + (c * 32 + lane) * 8;
+      float dx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dx[i] = rs * (dyg[c][i] - c1 - xh[c][i] * c2);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dr[c][i] += dx[i];
+        store8(p.dres_out + off, dr[c]);
+        if (want_p) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { dr[c][i] *= sc; acc_p[c][i] += dr[c][i]; }
+          if (p.dyb != nullptr) store8(p.dyb + off, dr[c]);
+        }
+      } else {
+        store8(p.dx + off, dx);
+      }
+    }
+  }
+  // combine the 4 warps' column partials in shared memory, then one atomic per column per block
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = (c * 32 + lane) * 8 + i;
+      atomicAdd(&sacc[0][col], acc_g[c][i]);
+      atomicAdd(&sacc[1][col], acc_b[c][i]);
+      if (want_p) atomicAdd(&sacc[2][col], acc_p[c][i]);
+    }
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < C; col += 128) {
+    atomicAdd(p.dgamma + col, sacc[0][col]);
+    atomicAdd(p.dbeta + col, sacc[1][col]);
+    if (want_p && p.dbias_prev != nullptr) atomicAdd(p.dbias_prev + col, sacc[2][col]);
+  }
+}
+
+// Wide rows (FFN LayerNorm + GELU backward, C = 3072 / 4096): one 128-thread block per row, each warp owns a contiguous
+// quarter of the columns (NCH chunks of 8 per lane, register accumulators), one block barrier per row (double-buffered
+// partials), next row's packed operands prefetched.  Blocks are small and independent, so several rows are in flight per SM.
+template <int NCH>
+__global__ void __launch_bounds__(128) ln_bwd_wide_kernel(const LnBwdParams p) {
+  constexpr int C = NCH * 4 * 256;
+  __shared__ float red[2][4][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col0 = warp * NCH * 256 + lane * 8;
+  float g[NCH][8], acc_g[NCH][8], acc_b[NCH][8], acc_p[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    load8(p.gamma + col0 + c * 256, g[c]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc_g[c][i] = 0.f; acc_b[c][i] = 0.f; acc_p[c][i] = 0.f; }
+  }
+  uint4 ndy[NCH], nu[NCH];
+  float nmu = 0.f, nrs = 0.f;
+  auto prefetch = [&](long long row) {
+    if (row < p.R) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const long long off = row * C + col0 + c * 256;
+        ndy[c] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.dy) + off));
+        nu[c] = __ldg(reinterpret_cast<const uint4*>(p.u + off));
+      }
+      nmu = __ldg(p.mean + row);
+      nrs = __ldg(p.rstd + row);
+    }
+  };
+  prefetch(blockIdx.x);
+  int par = 0;
+  for (long long row = blockIdx.x; row < p.R; row += gridDim.x, par ^= 1) {
+    uint4 cdy[NCH], cu[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { cdy[c] = ndy[c]; cu[c] = nu[c]; }
+    const float mu = nmu, rs = nrs;
+    prefetch(row + gridDim.x);
+    float xh[NCH][8], dyg[NCH][8], gg[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      unpack8(cu[c], cu[c], false, xh[c]);
+      unpack8(cdy[c], cdy[c], false, dyg[c]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float gv;
+        gg[c][i] = gelu_fwd_grad(xh[c][i], gv);
+        xh[c][i] = (gv - mu) * rs;
+        acc_g[c][i] += dyg[c][i] * xh[c][i];
+        acc_b[c][i] += dyg[c][i];
+        dyg[c][i] *= g[c][i];
+        s1 += dyg[c][i];
+        s2 += dyg[c][i] * xh[c][i];
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) { red[par][warp][0] = s1; red[par][warp][1] = s2; }
+    __syncthreads();
+    const float c1 = (red[par][0][0] + red[par][1][0] + red[par][2][0] + red[par][3][0]) * (1.0f / C);
+    const float c2 = (red[par][0][1] + red[par][1][1] + red[par][2][1] + red[par][3][1]) * (1.0f / C);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float dx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dx[i] = rs * (dyg[c][i] - c1 - xh[c][i] * c2) * gg[c][i];
+        acc_p[c][i] += dx[i];
+      }
+      store8(p.dx + row * C + col0 + c * 256, dx);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = col0 + c * 256 + i;
+      atomicAdd(p.dgamma + col, acc_g[c][i]);
+      atomicAdd(p.dbeta + col, acc_b[c][i]);
+      if (p.dbias_prev != nullptr) atomicAdd(p.dbias_prev + col, acc_p[c][i]);
+    }
+  }
+}
+
+template <int MODE, bool DYF32>
+static bool dispatch_ln_bwd_warp(const LnBwdParams& p, cudaStream_t st) {
+  long long blocks = (p.R + 3) / 4;
+  const long long cap = (long long)sm_count() * 3;
+  if (blocks > cap) blocks = cap;
+  switch (p.C) {
+    case 256: ln_bwd_warp_kernel<MODE, DYF32, 1><<<(unsigned)blocks, 128, 0, st>>>(p); return true;
+    case 768: ln_bwd_warp_kernel<MODE, DYF32, 3><<<(unsigned)blocks, 128, 0, st>>>(p); return true;
+    case 1024: ln_bwd_warp_kernel<MODE, DYF32, 4><<<(unsigned)blocks, 128, 0, st>>>(p); return true;
+    default: return false;
   }
 }
 
@@ -532,10 +721,36 @@ extern "C" int simvgb_ln_bwd(const simvgb_ln_bwd_args* a, void* stream) {
   const int grid = ln_grid(a->rows, rpb);
   const size_t sm = sizeof(float) * rpb * W * kLnMaxRB * 2;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (p.mode == 0 && p.dy_f32) ln_bwd_kernel<0, true><<<grid, threads, sm, st>>>(p);
-  else if (p.mode == 0) ln_bwd_kernel<0, false><<<grid, threads, sm, st>>>(p);
-  else if (p.mode == 1) ln_bwd_kernel<1, false><<<grid, threads, sm, st>>>(p);
-  else ln_bwd_kernel<2, false><<<grid, threads, sm, st>>>(p);
+  if (p.mode != 2) {   // narrow rows: warp-per-row kernel
+    bool done;
+    if (p.mode == 0 && p.dy_f32) done = dispatch_ln_bwd_warp<0, true>(p, st);
+    else if (p.mode == 0) done = dispatch_ln_bwd_warp<0, false>(p, st);
+    else done = dispatch_ln_bwd_warp<1, false>(p, st);
+    if (done) {
+      SIMVGB_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
+  if (p.mode == 2 && !p.dy_f32 && (p.C == 3072 || p.C == 4096)) {
+    long long blocks = p.R;
+    const long long cap = (long long)sm_count() * 2;   // 255 registers x 128 threads: two resident blocks per SM
+    if (blocks > cap) blocks = cap;
+    if (p.C == 3072) ln_bwd_wide_kernel<3><<<(unsigned)blocks, 128, 0, st>>>(p);
+    else ln_bwd_wide_kernel<4><<<(unsigned)blocks, 128, 0, st>>>(p);
+    SIMVGB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  // <= 384 threads per block (C <= 3072): cap registers so two blocks are resident per SM (the kernel is latency-bound)
+#define SIMVGB_LN_BWD(M, F)                                                        \
+  do {                                                                             \
+    if (threads <= 384) ln_bwd_kernel<M, F, 384, 2><<<grid, threads, sm, st>>>(p); \
+    else if (threads <= 512) ln_bwd_kernel<M, F, 512, 1><<<grid, threads, sm, st>>>(p); \
+    else ln_bwd_kernel<M, F, 1024, 1><<<grid, threads, sm, st>>>(p);               \
+  } while (0)
+  if (p.mode == 0 && p.dy_f32) SIMVGB_LN_BWD(0, true);
+  else if (p.mode == 0) SIMVGB_LN_BWD(0, false);
+  else if (p.mode == 1) SIMVGB_LN_BWD(1, false);
+  else SIMVGB_LN_BWD(2, false);
   SIMVGB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -330,13 +330,10 @@ def encoder_forward(mod, image, ids, pad_mask, save):
             xmid = K.gemm(a, G.wb["o_w"], Rs[g], D, D, epilogue=K.EPI_RESID, bias=G.w["o_b"], res=x[g], row_scale=dp1,
                           rows_per_scale=Ls[g])
             h2, m2, r2 = K.ln_fwd(xmid, G.w["ln2_w"], G.w["ln2_b"], eps)
-            # fc1 + bias + exact-erf GELU in the GEMM epilogue (ALU work hidden under the MMA main loop): u is kept for the
-            # backward, which recomputes gelu(u); the activation gl only lives until the FFN LayerNorm has consumed it.
-            u = torch.empty(Rs[g], F, device=image.device, dtype=bf16)
-            gl = torch.empty(Rs[g], F, device=image.device, dtype=bf16)
-            K.gemm(h2, G.wb["fc1_w"], Rs[g], F, D, epilogue=K.EPI_GELU, bias=G.w["fc1_b"], out=u, out2=gl)
-            f, mf, rf = K.ln_fwd(gl, G.w["fl_w"], G.w["fl_b"], eps)
-            del gl
+            # fc1 + bias; the exact-erf GELU is applied inside the FFN LayerNorm kernel (LN_F(gelu(u))) and recomputed in the
+            # backward, so the activation itself is never written to HBM.
+            u = K.gemm(h2, G.wb["fc1_w"], Rs[g], F, D, epilogue=K.EPI_BF16, bias=G.w["fc1_b"])
+            f, mf, rf = K.ln_fwd(u, G.w["fl_w"], G.w["fl_b"], eps, gelu=True)
             xn = K.gemm(f, G.wb["fc2_w"], Rs[g], D, F, epilogue=K.EPI_RESID, bias=G.w["fc2_b"], res=xmid, row_scale=dp2,
                         rows_per_scale=Ls[g])
             if save:
