@@ -101,9 +101,9 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
     mbar_init(dq_empty, 4);
     fence_barrier_init();
   }
-  if (threadIdx.x == 64) {
-    if (kt >= g.nfull) build_tile_mask(kmask, g, p.pad, b, kt);
-    else kmask[0] = kmask[1] = kmask[2] = kmask[3] = 0xffffffffu;
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {   // warps 2-5
+    if (kt >= g.nfull) build_tile_mask(kmask, g, p.pad, b, kt, threadIdx.x - 64);
+    else if (threadIdx.x < 64 + 4) kmask[threadIdx.x - 64] = 0xffffffffu;
   }
   if (warp == 0) {
     tmem_alloc(tmem_slot, 512);

@@ -65,19 +65,15 @@ __device__ __forceinline__ void load_virtual_tile(uint8_t* dst, uint64_t* bar, c
   }
 }
 
-// 128-bit validity mask of virtual tile t (bit j = position t*128+j is a real, unpadded token).
+// 128-bit validity mask of virtual tile t (bit j = position t*128+j is a real, unpadded token).  Called by 128
+// consecutive threads (4 full warps): thread j tests position j, one ballot per warp writes one mask word.
 __device__ __forceinline__ void build_tile_mask(uint32_t* mask4, const AttnGeom& g, const unsigned char* pad,
-                                                int b, int t) {
-  for (int w = 0; w < 4; ++w) {
-    uint32_t bits = 0;
-    for (int j = 0; j < 32; ++j) {
-      const int v = t * kTile + w * 32 + j;
-      bool ok = v < g.Lv;
-      if (!ok && v >= g.T0 && v < g.T0 + g.Lt) ok = (pad == nullptr) || (pad[b * g.Lt + (v - g.T0)] == 0);
-      bits |= (ok ? 1u : 0u) << j;
-    }
-    mask4[w] = bits;
-  }
+                                                int b, int t, int j /*0..127*/) {
+  const int v = t * kTile + j;
+  bool ok = v < g.Lv;
+  if (!ok && v >= g.T0 && v < g.T0 + g.Lt) ok = (pad == nullptr) || (pad[b * g.Lt + (v - g.T0)] == 0);
+  const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+  if ((j & 31) == 0) mask4[j >> 5] = bits;
 }
 
 // Byte offset of (row r, 16-byte chunk c) inside a [128 x 128] bf16 tile stored as two [128 x 64] 128B-swizzled

@@ -13,6 +13,8 @@
 //   O += P V_j    : P (bf16) written by the softmax threads into 128B-swizzled smem, V_j read MN-major straight
 //                   from its token-major TMA tile; O in TMEM columns [128,192)
 // Online softmax with lazy rescaling (O is only rescaled when a row max grows by more than 2^8).
+#include <stdlib.h>
+
 #include "attn_common.cuh"
 #include "simvg_b200.h"
 
@@ -30,6 +32,7 @@ struct AttnFwdParams {
   bf16* out_v;               // [B*Lv, D]
   bf16* out_t;               // [B*Lt, D]
   float* lse;                // [B, H, ntiles*128]  log2-domain logsumexp of each query row
+  int dbg;                   // timing ablations (SIMVGB_ATTN_DEBUG, tools/attn_ablate.py); 0 in production
 };
 
 __device__ __forceinline__ void pair_sync(int quarter) {   // the two softmax warps that share a TMEM lane quarter
@@ -76,9 +79,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 2) {
-    const int t = g.nfull + (threadIdx.x - 64);
-    if (t < nk) build_tile_mask(masks + 4 * (threadIdx.x - 64), g, p.pad, b, t);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {   // warps 2-5: first partial tile, warps 6-9: second partial tile
+    const int which = (threadIdx.x - 64) >> 7;
+    const int t = g.nfull + which;
+    if (t < nk) build_tile_mask(masks + 4 * which, g, p.pad, b, t, (threadIdx.x - 64) & 127);
   }
   if (warp == 0) {
     tmem_alloc(tmem_slot, 256);
@@ -133,6 +137,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
       tc_fence_after();
       const uint64_t dv = dKV_mn + slot * (kTileBytes >> 4);
       if (elect_one()) {
+        if (!(p.dbg & 8))
 #pragma unroll
         for (int k = 0; k < kTile / 16; ++k)
           umma_f16_ss(tmO, dP + (k >> 2) * (kTileBytes >> 4) + (k & 3) * 2, dv + k * 128, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
@@ -155,9 +160,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
       const bool partial = j >= g.nfull;
       const uint32_t* mk = masks + 4 * (j - g.nfull) + half * 2;
       uint32_t va[32], vb[32];
-      tmem_ld32(tmS + lane_base + col_base, va);
-      tmem_ld32(tmS + lane_base + col_base + 32, vb);
-      tmem_wait_ld();
+      if (!(p.dbg & 1)) {
+        tmem_ld32(tmS + lane_base + col_base, va);
+        tmem_ld32(tmS + lane_base + col_base + 32, vb);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { va[i] = 0; vb[i] = 0; }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);   // scores are in registers: the MMA warp may overwrite S with Q K_{j+1}^T
@@ -173,9 +183,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
 #pragma unroll
       for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
       float* xm = xchg + (j & 1) * 256;
-      xm[half * 128 + r] = mx;
-      pair_sync(quarter);
-      mx = fmaxf(mx, xm[(half ^ 1) * 128 + r]) * kLog2e;
+      if (!(p.dbg & 16)) {
+        xm[half * 128 + r] = mx;
+        pair_sync(quarter);
+        mx = fmaxf(mx, xm[(half ^ 1) * 128 + r]);
+      }
+      mx *= kLog2e;
       const bool need = mx > m + 8.0f;       // lazy rescale threshold (log2 units); true on the first tile
       const float m_use = need ? mx : m;
       const float alpha = need ? ex2_approx(m - m_use) : 1.0f;
@@ -195,13 +208,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float pa = ex2_approx(fmaf(__uint_as_float(va[i]), kLog2e, -m_use));
-        const float pb = ex2_approx(fmaf(__uint_as_float(vb[i]), kLog2e, -m_use));
+        const float pa = (p.dbg & 2) ? __uint_as_float(va[i]) : ex2_approx(fmaf(__uint_as_float(va[i]), kLog2e, -m_use));
+        const float pb = (p.dbg & 2) ? __uint_as_float(vb[i]) : ex2_approx(fmaf(__uint_as_float(vb[i]), kLog2e, -m_use));
         sum += pa + pb;
         va[i] = __float_as_uint(pa);
         vb[i] = __float_as_uint(pb);
       }
       const uint32_t aP = smem_u32(sP);
+      if (!(p.dbg & 4))
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         st_shared_v4(aP + swz_off(r, half * 8 + q4),
@@ -295,6 +309,10 @@ extern "C" int simvgb_attn_fwd(const simvgb_attn_args* a, void* stream) {
   p.out_v = reinterpret_cast<bf16*>(a->out_v);
   p.out_t = reinterpret_cast<bf16*>(a->out_t);
   p.lse = a->lse;
+  {
+    static const int dbg_env = [] { const char* e = getenv("SIMVGB_ATTN_DEBUG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg_env;
+  }
   CUtensorMap full, tail, text;
   if (make_attn_maps(&full, &tail, &text, p.g, a->qkv_v, a->qkv_t, 3 * D)) return -1;
   static bool attr_set = false;

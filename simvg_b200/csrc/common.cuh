@@ -92,6 +92,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef SIMVGB_BACKOFF_NS
+    __nanosleep(SIMVGB_BACKOFF_NS);   // waiting warps yield their issue slots instead of spinning
+#endif
     if (++spins > SIMVGB_SPIN_LIMIT) {
       printf("simvgb: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x,
              threadIdx.x, smem_u32(bar), parity);
