@@ -16,6 +16,12 @@
 #include <stdlib.h>
 
 #include "attn_common.cuh"
+
+#ifdef SIMVGB_ATTN_ABLATE   // timing ablations (tools/attn_ablate.py): build with -DSIMVGB_ATTN_ABLATE
+#define SIMVGB_DBG(p) ((p).dbg)
+#else
+#define SIMVGB_DBG(p) 0
+#endif
 #include "simvg_b200.h"
 
 namespace simvgb {
@@ -175,13 +181,13 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       tc_fence_after();
       const uint64_t dsk = dS_kmaj0 + pb * 2 * kTileStep, dsm = dS_mn0 + pb * 2 * kTileStep, dpm = dP_mn0 + pb * 2 * kTileStep;
       const uint64_t dqm = dQ_mn0 + s * kTileStep, dom = dO_mn0 + s * kTileStep;
-      if (!(p.dbg & 16) && elect_one()) {
+      if (!(SIMVGB_DBG(p) & 16) && elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // dQ_i = dS K_j        (A: dS K-major, B: K_j MN-major)
           umma_f16_ss(tmdQ, dsk + (k >> 2) * kTileStep + (k & 3) * 2, dK_mn + k * 128, idesc_dq, k > 0);
       }
       if (elect_one()) umma_commit(dq_full);
-      if (!(p.dbg & 16) && elect_one()) {
+      if (!(SIMVGB_DBG(p) & 16) && elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // dV_j += P^T dO_i     (A: P MN-major, B: dO_i MN-major)
           umma_f16_ss(tmdV, dpm + k * 128, dom + k * 128, idesc_dkv, (i > 0 || k > 0) ? 1u : 0u);
@@ -224,7 +230,7 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       for (int cc = 0; cc < 2; ++cc) {
         const int c = half * 2 + cc;
         uint32_t sv[32], dv[32];
-        if (!(p.dbg & 4)) {
+        if (!(SIMVGB_DBG(p) & 4)) {
           tmem_ld32(tmS + lane_base + c * 32, sv);
           tmem_ld32(tmdP + lane_base + c * 32, dv);
           tmem_wait_ld();
@@ -233,7 +239,7 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
           for (int t = 0; t < 32; ++t) { sv[t] = 0; dv[t] = 0; }
         }
         float pr[32], ds[32];
-        if (p.dbg & 2) {
+        if (SIMVGB_DBG(p) & 2) {
 #pragma unroll
           for (int t = 0; t < 32; ++t) { pr[t] = __uint_as_float(sv[t]); ds[t] = __uint_as_float(dv[t]); }
         } else if (!slow) {
@@ -312,7 +318,7 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_empty);
-      if (dst != nullptr && !(p.dbg & 1)) {
+      if (dst != nullptr && !(SIMVGB_DBG(p) & 1)) {
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4)
           red_add_v4(dst + 4 * q4, __uint_as_float(v0[4 * q4]), __uint_as_float(v0[4 * q4 + 1]),

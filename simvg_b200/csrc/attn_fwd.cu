@@ -16,13 +16,22 @@
 #include <stdlib.h>
 
 #include "attn_common.cuh"
+
+#ifdef SIMVGB_ATTN_ABLATE   // timing ablations (tools/attn_ablate.py): build with -DSIMVGB_ATTN_ABLATE
+#define SIMVGB_DBG(p) ((p).dbg)
+#else
+#define SIMVGB_DBG(p) 0
+#endif
 #include "simvg_b200.h"
 
 namespace simvgb {
 
+static long long* g_fwd_trace = nullptr;
+
 constexpr int kFwdThreads = 320;
 constexpr int kSoftmaxThreads = 256;
-constexpr int kSlots = 3;  // K/V ring: K_j, V_j, K_{j+1} ...
+constexpr int kSlots = 3;  // staging tiles: K double-buffered (slots 0,1: K_{j+1} is prefetched a full tile ahead), V single (slot 2:
+                           // its load hides behind the softmax of the same tile)
 constexpr int kFwdSmem = kTileBytes /*Q*/ + 2 * kTileBytes /*P*/ + kSlots * kTileBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*row-max exchange*/;
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -33,6 +42,7 @@ struct AttnFwdParams {
   bf16* out_t;               // [B*Lt, D]
   float* lse;                // [B, H, ntiles*128]  log2-domain logsumexp of each query row
   int dbg;                   // timing ablations (SIMVGB_ATTN_DEBUG, tools/attn_ablate.py); 0 in production
+  long long* ts;             // optional clock64 trace of CTA (0,0,0) (tools/attn_trace.py)
 };
 
 __device__ __forceinline__ void pair_sync(int quarter) {   // the two softmax warps that share a TMEM lane quarter
@@ -49,7 +59,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   uint8_t* sKV = smem + 3 * kTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (3 + kSlots) * kTileBytes);
   uint64_t* q_full = bars;
-  uint64_t* slot_full = bars + 1;             // [kSlots]
+  uint64_t* slot_full = bars + 1;             // [kSlots]  0,1 = K ring, 2 = V
   uint64_t* slot_empty = bars + 1 + kSlots;   // [kSlots]
   uint64_t* s_full = bars + 1 + 2 * kSlots;
   uint64_t* s_empty = s_full + 1;
@@ -99,12 +109,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
     if (lane == 0) {
       const int colq = h * kHeadDim, colk = g.D + h * kHeadDim, colv = 2 * g.D + h * kHeadDim;
       load_virtual_tile(sQ, q_full, g, &map_full, &map_tail, &map_text, qt, colq, b);
-      for (int n = 0; n < 2 * nk; ++n) {
-        const int slot = n % kSlots;
-        const uint32_t ph = (n / kSlots) & 1;
-        mbar_wait(&slot_empty[slot], ph ^ 1);
-        load_virtual_tile(sKV + slot * kTileBytes, &slot_full[slot], g, &map_full, &map_tail, &map_text, n >> 1,
-                          (n & 1) ? colv : colk, b);
+      auto load_k = [&](int j) {
+        const int slot = j & 1;
+        mbar_wait(&slot_empty[slot], ((j >> 1) & 1) ^ 1);       // freed when S_{j-2} retired
+        load_virtual_tile(sKV + slot * kTileBytes, &slot_full[slot], g, &map_full, &map_tail, &map_text, j, colk, b);
+      };
+      load_k(0);
+      for (int j = 0; j < nk; ++j) {
+        if (j + 1 < nk) load_k(j + 1);
+        mbar_wait(&slot_empty[2], (j & 1) ^ 1);                 // freed when P V_{j-1} retired
+        load_virtual_tile(sKV + 2 * kTileBytes, &slot_full[2], g, &map_full, &map_tail, &map_text, j, colv, b);
       }
     }
   } else if (warp == 1) {
@@ -114,8 +128,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
     const uint64_t dQ = umma_smem_desc(smem_u32(sQ), 16, 1024), dP = umma_smem_desc(smem_u32(sP), 16, 1024);
     const uint64_t dKV_k = umma_smem_desc(smem_u32(sKV), 16, 1024), dKV_mn = umma_smem_desc(smem_u32(sKV), 8192, 1024);
     auto issue_s = [&](int j) {
-      const int n = 2 * j, slot = n % kSlots;
-      mbar_wait(&slot_full[slot], (n / kSlots) & 1);
+      const int slot = j & 1;
+      mbar_wait(&slot_full[slot], (j >> 1) & 1);
       tc_fence_after();
       const uint64_t dk = dKV_k + slot * (kTileBytes >> 4);
       if (elect_one()) {
@@ -126,18 +140,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
       }
       __syncwarp();
     };
+    const bool trace = p.ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
     mbar_wait(q_full, 0);
     issue_s(0);
     for (int j = 0; j < nk; ++j) {
+      if (trace) p.ts[j * 8 + 0] = clock64();
       mbar_wait(s_empty, j & 1);  // softmax has consumed S_j
+      if (trace) p.ts[j * 8 + 1] = clock64();
       if (j + 1 < nk) issue_s(j + 1);
-      const int n = 2 * j + 1, slot = n % kSlots;
+      if (trace) p.ts[j * 8 + 2] = clock64();
+      const int slot = 2;
       mbar_wait(p_full, j & 1);
-      mbar_wait(&slot_full[slot], (n / kSlots) & 1);
+      if (trace) p.ts[j * 8 + 3] = clock64();
+      mbar_wait(&slot_full[slot], j & 1);
+      if (trace) p.ts[j * 8 + 4] = clock64();
       tc_fence_after();
       const uint64_t dv = dKV_mn + slot * (kTileBytes >> 4);
       if (elect_one()) {
-        if (!(p.dbg & 8))
+        if (!(SIMVGB_DBG(p) & 8))
 #pragma unroll
         for (int k = 0; k < kTile / 16; ++k)
           umma_f16_ss(tmO, dP + (k >> 2) * (kTileBytes >> 4) + (k & 3) * 2, dv + k * 128, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
@@ -145,6 +165,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
         umma_commit(pv_done);
       }
       __syncwarp();
+      if (trace) p.ts[j * 8 + 5] = clock64();
     }
   } else {
     // ------------------------------ softmax: thread = (query row, 64-column half) ------------------------------
@@ -160,7 +181,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
       const bool partial = j >= g.nfull;
       const uint32_t* mk = masks + 4 * (j - g.nfull) + half * 2;
       uint32_t va[32], vb[32];
-      if (!(p.dbg & 1)) {
+      if (!(SIMVGB_DBG(p) & 1)) {
         tmem_ld32(tmS + lane_base + col_base, va);
         tmem_ld32(tmS + lane_base + col_base + 32, vb);
         tmem_wait_ld();
@@ -183,7 +204,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
 #pragma unroll
       for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
       float* xm = xchg + (j & 1) * 256;
-      if (!(p.dbg & 16)) {
+      if (!(SIMVGB_DBG(p) & 16)) {
         xm[half * 128 + r] = mx;
         pair_sync(quarter);
         mx = fmaxf(mx, xm[(half ^ 1) * 128 + r]);
@@ -208,14 +229,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float pa = (p.dbg & 2) ? __uint_as_float(va[i]) : ex2_approx(fmaf(__uint_as_float(va[i]), kLog2e, -m_use));
-        const float pb = (p.dbg & 2) ? __uint_as_float(vb[i]) : ex2_approx(fmaf(__uint_as_float(vb[i]), kLog2e, -m_use));
+        const float pa = (SIMVGB_DBG(p) & 2) ? __uint_as_float(va[i]) : ex2_approx(fmaf(__uint_as_float(va[i]), kLog2e, -m_use));
+        const float pb = (SIMVGB_DBG(p) & 2) ? __uint_as_float(vb[i]) : ex2_approx(fmaf(__uint_as_float(vb[i]), kLog2e, -m_use));
         sum += pa + pb;
         va[i] = __float_as_uint(pa);
         vb[i] = __float_as_uint(pb);
       }
       const uint32_t aP = smem_u32(sP);
-      if (!(p.dbg & 4))
+      if (!(SIMVGB_DBG(p) & 4))
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         st_shared_v4(aP + swz_off(r, half * 8 + q4),
@@ -312,6 +333,7 @@ extern "C" int simvgb_attn_fwd(const simvgb_attn_args* a, void* stream) {
   {
     static const int dbg_env = [] { const char* e = getenv("SIMVGB_ATTN_DEBUG"); return e ? atoi(e) : 0; }();
     p.dbg = dbg_env;
+    p.ts = g_fwd_trace;
   }
   CUtensorMap full, tail, text;
   if (make_attn_maps(&full, &tail, &text, p.g, a->qkv_v, a->qkv_t, 3 * D)) return -1;
@@ -330,3 +352,5 @@ extern "C" int simvgb_attn_lse_stride(int Lv, int Lt) {
   simvgb::AttnGeom g = simvgb::make_attn_geom(1, 1, Lv, Lt, 64);
   return g.ntiles * simvgb::kTile;
 }
+
+extern "C" void simvgb_debug_attn_fwd_trace(long long* buf) { simvgb::g_fwd_trace = buf; }

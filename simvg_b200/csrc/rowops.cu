@@ -538,10 +538,10 @@ __global__ void colsum_kernel(const TIn* __restrict__ in, float* __restrict__ ou
   // block = 256 threads: 32 column-chunks (8 cols each) x 8 row lanes
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + cx) * 8;
-  if (col >= C) return;
+  const bool col_ok = col < C;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long stride = (long long)gridDim.y * 8;
-  for (long long row = (long long)blockIdx.y * 8 + ry; row < R; row += 4 * stride) {
+  for (long long row = (long long)blockIdx.y * 8 + ry; col_ok && row < R; row += 4 * stride) {
     float v[4][8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {     // 4 independent loads in flight per thread
@@ -560,8 +560,19 @@ __global__ void colsum_kernel(const TIn* __restrict__ in, float* __restrict__ ou
     }
   }
   if (out != nullptr) {
+    // combine the block's 8 row lanes in shared memory, then one atomic per column per block
+    __shared__ float part[8][32 * 8 + 1];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(out + col + i, acc[i]);
+    for (int i = 0; i < 8; ++i) part[ry][cx * 8 + i] = acc[i];
+    __syncthreads();
+    const int c = threadIdx.x;   // 256 threads <-> 256 columns of this block
+    const int gc = blockIdx.x * 256 + c;
+    if (gc < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += part[r][c];
+      atomicAdd(out + gc, t);
+    }
   }
 }
 
@@ -763,7 +774,7 @@ extern "C" int simvgb_colsum(const void* in, int in_is_bf16, float* out, void* o
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid((C / 8 + 31) / 32, 1);
   long long gy = (rows + 7) / 8;
-  const long long cap = (long long)sm_count() * 8 / grid.x + 1;
+  const long long cap = (long long)sm_count() * 6 / grid.x + 1;
   grid.y = (unsigned)(gy < cap ? gy : cap);
   const int rps = rows_per_scale > 0 ? rows_per_scale : 1;
   if (in_is_bf16)
