@@ -16,6 +16,16 @@ from simvg_b200.core.box_ops import box_cxcywh_to_xyxy, generalized_box_iou
 from simvg_b200.utils.distributed import get_world_size, is_dist_avail_and_initialized
 
 
+class BatchedTargets(list):
+    """Per-sample target dicts (the reference's format) that also carry their batched tensors: `boxes` [B,4], `labels` [B]
+    and optionally `weight` [B] — present when every sample has exactly one target (REC).  Lets the criterion skip all
+    per-sample indexing (hundreds of tiny kernel launches per step in the reference, criterion.py:114-121,170-172)."""
+
+    def __init__(self, items, boxes, labels, weight=None):
+        super().__init__(items)
+        self.boxes, self.labels, self.weight = boxes, labels, weight
+
+
 class HungarianMatcher(nn.Module):
     def __init__(self, cost_class=1.0, cost_bbox=1.0, cost_giou=1.0, cost_class_type="ce_cost", alpha=0.25, gamma=2.0):
         super().__init__()
@@ -106,7 +116,40 @@ class SetCriterion(nn.Module):
     def get_loss(self, loss, outputs, targets, indices, num_boxes):
         return {"class": self.loss_labels, "boxes": self.loss_boxes}[loss](outputs, targets, indices, num_boxes)
 
+    def _forward_rec(self, outputs, targets):
+        """One query, one target per sample: the assignment is the identity and every loss is a batched expression."""
+        from simvg_b200.core.box_ops import aligned_iou_giou
+        num_boxes = float(len(targets))
+        if is_dist_avail_and_initialized():
+            nb = torch.as_tensor([num_boxes], dtype=torch.float, device=outputs["pred_logits"].device)
+            torch.distributed.all_reduce(nb)
+            num_boxes = nb.item()
+        num_boxes = max(num_boxes / get_world_size(), 1.0)
+        tcls = targets.labels.view(-1, 1)
+        tbox = targets.boxes
+
+        def one(logits, boxes, suffix):
+            if self.loss_class_type == "ce_loss":
+                lc = F.cross_entropy(logits.transpose(1, 2), tcls, self.empty_weight)
+            else:  # weighted_ce_loss with every query matched: per-query weight 1 (criterion.py:128-137)
+                lc = F.cross_entropy(logits.transpose(1, 2), tcls, self.empty_weight, reduction="none").mean(-1).sum()
+            src = boxes[:, 0]
+            l1 = F.l1_loss(src, tbox, reduction="none")
+            giou = 1 - aligned_iou_giou(box_cxcywh_to_xyxy(src), box_cxcywh_to_xyxy(tbox))[1]
+            if self.loss_class_type == "weighted_ce_loss":
+                l1 = l1.sum(-1) * targets.weight
+                giou = giou * targets.weight
+            return {"loss_class" + suffix: lc, "loss_bbox" + suffix: l1.sum() / num_boxes, "loss_giou" + suffix: giou.sum() / num_boxes}
+
+        losses = one(outputs["pred_logits"], outputs["pred_boxes"], "")
+        for i, aux in enumerate(outputs.get("aux_outputs", [])):
+            losses.update(one(aux["pred_logits"], aux["pred_boxes"], "_%d" % i))
+        return losses
+
     def forward(self, outputs, targets, return_indices=False):
+        if (isinstance(targets, BatchedTargets) and not return_indices and outputs["pred_logits"].shape[1] == 1
+                and self.loss_class_type != "focal_loss" and list(self.losses) == ["class", "boxes"]):
+            return self._forward_rec(outputs, targets)
         main = {k: v for k, v in outputs.items() if k != "aux_outputs"}
         indices = self.matcher(main, targets)
         num_boxes = float(sum(len(t["labels"]) for t in targets))   # host-side count: no .item() sync

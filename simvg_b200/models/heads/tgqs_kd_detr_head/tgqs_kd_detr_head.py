@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from simvg_b200 import ops
 from simvg_b200.core.box_ops import aligned_iou_giou, box_cxcywh_to_xyxy, box_iou, box_xyxy_to_cxcywh
-from simvg_b200.core.criterion.criterion import HungarianMatcher, SetCriterion
+from simvg_b200.core.criterion.criterion import BatchedTargets, HungarianMatcher, SetCriterion
 from simvg_b200.models.builder import HEADS
 from simvg_b200.models.heads.utils import MLP, PositionEmbeddingSine1D
 from simvg_b200.structures import Boxes, Instances
@@ -122,7 +122,8 @@ class TextGuidedQuerySelectKDDETRHead(nn.Module):
                                 dtype=torch.float).to(dev, non_blocking=True)
             gt = box_xyxy_to_cxcywh(torch.stack([t.to(dev) for t in targets]).float() / whwh).float()  # [B, 4]
             zeros = torch.zeros(len(targets), 1, dtype=torch.int64, device=dev)
-            new_gt = [{"labels": zeros[i], "boxes": gt[i:i + 1]} for i in range(len(targets))]
+            new_gt = BatchedTargets([{"labels": zeros[i], "boxes": gt[i:i + 1]} for i in range(len(targets))],
+                                    boxes=gt, labels=zeros[:, 0])
         else:
             new_gt = []
             for tb, meta in zip(targets, img_metas):
@@ -146,7 +147,8 @@ class TextGuidedQuerySelectKDDETRHead(nn.Module):
                 iou, _ = aligned_iou_giou(box_cxcywh_to_xyxy(boxes[:, 0]), box_cxcywh_to_xyxy(gt))
                 wgt = scores[:, 0, 0] * iou                                               # [B]
                 zeros = torch.zeros(len(targets), 1, dtype=torch.int64, device=dev)
-                new_pred = [{"labels": zeros[i], "boxes": boxes[i], "weight": wgt[i:i + 1]} for i in range(len(targets))]
+                new_pred = BatchedTargets([{"labels": zeros[i], "boxes": boxes[i], "weight": wgt[i:i + 1]}
+                                           for i in range(len(targets))], boxes=boxes[:, 0], labels=zeros[:, 0], weight=wgt)
             else:
                 indices = self.matcher(decoder_branch_output, new_gt)
                 for (i_p, i_t), pb, ps, tg in zip(indices, boxes, scores, new_gt):
@@ -259,7 +261,8 @@ class TextGuidedQuerySelectKDDETRHead(nn.Module):
             return c, b
 
         if "balanced_distill" in blw:
-            w = torch.mean(torch.cat([t["weight"] for t in targets_predict]))
+            w = targets_predict.weight.mean() if isinstance(targets_predict, BatchedTargets) and targets_predict.weight is not None \
+                else torch.mean(torch.cat([t["weight"] for t in targets_predict]))
             ct, bt = last_only(cls_tok, coord_tok)
             l_tok = blw["balanced_distill"]["token"] * sum(self.calc_loss(ct, bt, targets_gt).values()) * (1 - w)
             loss_dict["loss_tgt"] = l_tok

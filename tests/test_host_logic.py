@@ -166,6 +166,28 @@ def test_criterion_matches_oracle_on_cpu():
             assert torch.allclose(got[k], want[k], rtol=1e-6, atol=1e-7), (nq, k)
 
 
+def test_batched_rec_criterion_equals_generic_path():
+    """The one-query / one-box fast path (no per-sample indexing, no matcher) must reproduce the generic path exactly."""
+    from simvg_b200.core.criterion.criterion import BatchedTargets, HungarianMatcher, SetCriterion
+    torch.manual_seed(3)
+    B = 6
+    logits, boxes = torch.randn(3, B, 1, 2), torch.rand(3, B, 1, 4) * 0.4 + 0.2
+    gt = torch.rand(B, 4) * 0.3 + 0.3
+    wgt = torch.rand(B)
+    zeros = torch.zeros(B, 1, dtype=torch.int64)
+    plain = [{"labels": zeros[i], "boxes": gt[i:i + 1], "weight": wgt[i:i + 1]} for i in range(B)]
+    batched = BatchedTargets(plain, boxes=gt, labels=zeros[:, 0], weight=wgt)
+    out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1],
+           "aux_outputs": [{"pred_logits": a, "pred_boxes": b} for a, b in zip(logits[:-1], boxes[:-1])]}
+    for kind in ("ce_loss", "weighted_ce_loss"):
+        crit = SetCriterion(1, HungarianMatcher(1, 5.0, 2.0, "ce_cost"), {"loss_class": 1, "loss_bbox": 5.0, "loss_giou": 2.0},
+                            loss_class_type=kind, eos_coef=0.1)
+        a, b = crit(out, plain), crit(out, batched)
+        assert set(a) == set(b)
+        for k in a:
+            assert torch.allclose(a[k], b[k], rtol=1e-6, atol=1e-7), (kind, k, float(a[k]), float(b[k]))
+
+
 def test_get_predictions_matches_oracle_on_cpu():
     from oracle import simvg_oracle as O
     from simvg_b200.models.det_seg.mix_detr_mb import MIXDETRMB
