@@ -29,8 +29,8 @@ namespace simvgb {
 int make_attn_maps(CUtensorMap* full, CUtensorMap* tail, CUtensorMap* text, const AttnGeom& g, const void* base_v,
                    const void* base_t, int row_elems);
 
-constexpr int kBwdThreads = 448;
-constexpr int kComputeThreads = 256;
+constexpr int kBwdThreads = 704;        // TMA + MMA + 16 compute + 4 dQ warps
+constexpr int kComputeThreads = 512;    // four warps per TMEM lane quarter, one 32-column chunk each
 #ifndef SIMVGB_BWD_STAGES
 #define SIMVGB_BWD_STAGES 2
 #endif
@@ -79,10 +79,11 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
   uint64_t* s_full = bars + 1 + 2 * kQS;
   uint64_t* s_empty = s_full + 1;
   uint64_t* p_full = s_full + 2;
-  uint64_t* pds_done = s_full + 3;
-  uint64_t* dq_full = s_full + 4;
-  uint64_t* dq_empty = s_full + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+  uint64_t* pds_done = s_full + 3;   // [2]: one per P/dS buffer — a single barrier could advance two phases past a slow
+                                     // waiter (parity aliasing) once the buffers are double-buffered
+  uint64_t* dq_full = s_full + 5;
+  uint64_t* dq_empty = s_full + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 7);
   uint32_t* kmask = tmem_slot + 2;  // [4]
 
   const AttnGeom& g = p.g;
@@ -102,7 +103,8 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
     mbar_init(s_full, 1);
     mbar_init(s_empty, kComputeThreads / 32);   // one elected arrival per compute warp
     mbar_init(p_full, kComputeThreads / 32);
-    mbar_init(pds_done, 1);
+    mbar_init(&pds_done[0], 1);
+    mbar_init(&pds_done[1], 1);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 4);
     fence_barrier_init();
@@ -197,15 +199,16 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       }
       if (elect_one()) {
         umma_commit(&qdo_empty[s]);
-        umma_commit(pds_done);
+        umma_commit(&pds_done[pb]);
       }
       __syncwarp();
       if (trace) p.ts[i * 16 + 4] = clock64();
     }
-  } else if (warp < 10) {
+  } else if (warp < 18) {
     // ------------------------------ compute: P and dS ------------------------------
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;      // key columns [64*half, 64*half + 64)
+    const int chunk = (warp - 2) >> 2;     // key columns [32*chunk, 32*chunk + 32)
+    const int half = chunk;                // (chunks 0,1 also store dK columns [32*chunk, +32) at the end)
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
     const float* lse = p.lse + ((long long)b * g.H + h) * lse_stride;
@@ -221,19 +224,22 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       if (trace) p.ts[i * 16 + 8] = clock64();
       mbar_wait(s_full, i & 1);
       if (trace) p.ts[i * 16 + 9] = clock64();
-      if (i > 1) mbar_wait(pds_done, i & 1);   // MMAs of pair i-2 have finished reading this P/dS buffer
+      if (i > 1) mbar_wait(&pds_done[i & 1], ((i >> 1) + 1) & 1);   // MMAs of pair i-2 have finished reading this buffer
       if (trace) p.ts[i * 16 + 10] = clock64();
       const uint32_t aP = smem_u32(sP) + (i & 1) * 2 * kTileBytes;
       const uint32_t adS = smem_u32(sdS) + (i & 1) * 2 * kTileBytes;
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
+      {
+        const int c = chunk;
         uint32_t sv[32], dv[32];
         if (!(SIMVGB_DBG(p) & 4)) {
           tmem_ld32(tmS + lane_base + c * 32, sv);
           tmem_ld32(tmdP + lane_base + c * 32, dv);
           tmem_wait_ld();
+          // this warp's share of S / dP is in registers: release it now so S_{i+1} / dP_{i+1} overlap the math below
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty);
         } else {
 #pragma unroll
           for (int t = 0; t < 32; ++t) { sv[t] = 0; dv[t] = 0; }
@@ -272,19 +278,20 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       fence_proxy_async();   // this thread's P/dS stores -> async proxy
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(s_empty);
+        if (SIMVGB_DBG(p) & 4) mbar_arrive(s_empty);
         mbar_arrive(p_full);
       }
       if (trace) p.ts[i * 16 + 12] = clock64();
     }
     // dK_j -> dqkv[:, D + h*64 ...]   (each of the two warps of a quarter stores one 32-column half)
-    mbar_wait(pds_done, (nq - 1) & 1);
+    if (nq > 1) mbar_wait(&pds_done[nq & 1], ((nq - 2) >> 1) & 1);          // pair nq-2 ...
+    mbar_wait(&pds_done[(nq - 1) & 1], ((nq - 1) >> 1) & 1);              // ... and the last pair have retired
     tc_fence_after();
     const int kv = kt * kTile + r;
     bf16* dst = nullptr;
     if (kv < g.Lv) dst = p.dqkv_v + ((long long)b * g.Lv + kv) * (3 * g.D) + g.D + h * kHeadDim;
     else if (kv >= g.T0 && kv < g.T0 + g.Lt) dst = p.dqkv_t + ((long long)b * g.Lt + (kv - g.T0)) * (3 * g.D) + g.D + h * kHeadDim;
-    {
+    if (chunk < 2) {
       uint32_t v[32];
       tmem_ld32(tmdK + lane_base + half * 32, v);
       tmem_wait_ld();
@@ -329,7 +336,8 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
                      __uint_as_float(v1[4 * q4 + 2]), __uint_as_float(v1[4 * q4 + 3]));
       }
     }
-    mbar_wait(pds_done, (nq - 1) & 1);
+    if (nq > 1) mbar_wait(&pds_done[nq & 1], ((nq - 2) >> 1) & 1);          // pair nq-2 ...
+    mbar_wait(&pds_done[(nq - 1) & 1], ((nq - 1) >> 1) & 1);              // ... and the last pair have retired
     tc_fence_after();
     const int kv = kt * kTile + r;
     bf16* dst = nullptr;
