@@ -325,15 +325,41 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_empty);
-      if (dst != nullptr && !(SIMVGB_DBG(p) & 1)) {
+      // Lane pairs (2k, 2k+1) swap half of their row so that each red.v4 instruction has the two lanes of a pair writing
+      // adjacent 16-byte chunks of the SAME row: every L2 atomic operation then covers a full 32-byte sector (half as
+      // many L2 atomic operations as one-row-per-lane).  even lane keeps float4 #0,2,4,6 of its row and receives the same
+      // of the odd lane's row; the odd lane keeps / receives float4 #1,3,5,7.
+      if (!(SIMVGB_DBG(p) & 1)) {
+        const bool odd = lane & 1;
+        const unsigned long long my = reinterpret_cast<unsigned long long>(dst);
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, my, 1);
+        float* row_e = reinterpret_cast<float*>(odd ? other : my);   // row owned by the even lane of the pair
+        float* row_o = reinterpret_cast<float*>(odd ? my : other);   // row owned by the odd lane
+        auto flush_half = [&](const uint32_t (&v)[32], int col0) {
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4)
-          red_add_v4(dst + 4 * q4, __uint_as_float(v0[4 * q4]), __uint_as_float(v0[4 * q4 + 1]),
-                     __uint_as_float(v0[4 * q4 + 2]), __uint_as_float(v0[4 * q4 + 3]));
+          for (int q = 0; q < 4; ++q) {
+            float recv[4], own[4];
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4)
-          red_add_v4(dst + 32 + 4 * q4, __uint_as_float(v1[4 * q4]), __uint_as_float(v1[4 * q4 + 1]),
-                     __uint_as_float(v1[4 * q4 + 2]), __uint_as_float(v1[4 * q4 + 3]));
+            for (int e = 0; e < 4; ++e) {
+              // float4 indices 2q (even) and 2q+1 (odd) of this 32-column half: send the one the partner keeps
+              const uint32_t ev = v[4 * (2 * q) + e], ov = v[4 * (2 * q + 1) + e];
+              recv[e] = __uint_as_float(__shfl_xor_sync(0xffffffffu, odd ? ev : ov, 1));
+              own[e] = __uint_as_float(odd ? ov : ev);
+            }
+            const int col = col0 + 4 * (2 * q + (odd ? 1 : 0));
+            // instruction A: the even lane's row; instruction B: the odd lane's row
+            if (row_e != nullptr) {
+              if (odd) red_add_v4(row_e + col, recv[0], recv[1], recv[2], recv[3]);
+              else red_add_v4(row_e + col, own[0], own[1], own[2], own[3]);
+            }
+            if (row_o != nullptr) {
+              if (odd) red_add_v4(row_o + col, own[0], own[1], own[2], own[3]);
+              else red_add_v4(row_o + col, recv[0], recv[1], recv[2], recv[3]);
+            }
+          }
+        };
+        flush_half(v0, 0);
+        flush_half(v1, 32);
       }
     }
     if (nq > 1) mbar_wait(&pds_done[nq & 1], ((nq - 2) >> 1) & 1);          // pair nq-2 ...
