@@ -1,3 +1,6 @@
+// 2-CTA (cta_group::2) variant of the tcgen05 GEMM in gemm.cu: a cluster of two CTAs (two SMs of one TPC) owns a 256 x 256
+// output tile; each CTA stages its 128 rows of A and HALF of the B tile (so TMA writes and UMMA operand reads per SM drop
+// from ~192 B/clk to ~128 B/clk, the shared-memory limit that caps the 1-CTA kernel), the leader issues M=256 MMAs.
 // tcgen05 GEMM for sm_100a:  C[M,N] = epilogue(A(M,K) · B(N,K)^T), bf16 x bf16 -> fp32 (TMEM accumulators).
 //
 // Persistent, warp-specialised, one CTA per SM:
@@ -12,26 +15,23 @@
 // Replaces (reference = PyTorch eager -> cuBLAS): every nn.Linear on SimVG's hot path
 // (torchscale q/k/v/out_proj, fc1, fc2 — built at /root/reference/simvg/models/vis_encs/beit/beit3_base.py:57-63,112-121)
 // and its autograd backward.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "simvg_b200.h"
 
 namespace simvgb {
 
 constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int BK = 64;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;
 
-template <int BN>
-struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+struct Gemm2Cfg {
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = BM * BK * 2;        // 16 KB: this CTA's 128 rows of A
+  static constexpr int kBBytes = 128 * BK * 2;       // 16 KB: this CTA's half (128 rows) of the 256-wide B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN;  // 512 or 256
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 512;              // 2 x 256 fp32 columns (double-buffered accumulators)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
 struct GemmParams {
@@ -54,11 +54,12 @@ struct GemmParams {
 
 __device__ __forceinline__ float gelu_erf(float x) { return gelu_fwd(x); }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = Gemm2Cfg;
+  constexpr int BN = 256;
+  const uint32_t cta = cluster_ctarank();   // 0 = leader (issues the MMAs), 1 = peer
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -80,67 +81,70 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&full[s], 2);    // leader: expect_tx arrive + the peer's remote arrive
+      mbar_init(&empty[s], 1);   // multicast tcgen05.commit from the leader
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], kEpiWarps);
+      mbar_init(&acc_empty[s], 2 * kEpiWarps);   // epilogue warps of both CTAs arrive on the leader's barrier
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_2cta();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // shfl from a fixed lane => provably warp-uniform
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;   // m_tiles counts 256-row tiles
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         const int split = t % p.k_splits;
         const int mn = t / p.k_splits;
-        const int m0 = (mn / p.n_tiles) * BM;
-        const int n0 = (mn % p.n_tiles) * BN;
+        const int m0 = (mn / p.n_tiles) * 256 + cta * BM;       // this CTA's 128 rows of the 256-row tile
+        const int n0 = (mn % p.n_tiles) * BN + cta * (BN / 2);  // this CTA's half of the B tile
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          if (cta == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);   // both CTAs' bytes land on the leader's barrier
           uint8_t* a = smemA + stage * Cfg::kABytes;
           uint8_t* b = smemB + stage * Cfg::kBBytes;
           const int k0 = kb * BK;
           if (!p.a_mn) {
-            tma_load_2d(a, &tmA, &full[stage], k0, m0);  // box (64 k, 128 m)
+            tma_load_2d_2cta(a, &tmA, &full[stage], k0, m0);  // box (64 k, 128 m)
           } else {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i)            // boxes (64 m, 64 k)
-              tma_load_2d(a + i * 8192, &tmA, &full[stage], m0 + i * 64, k0);
+              tma_load_2d_2cta(a + i * 8192, &tmA, &full[stage], m0 + i * 64, k0);
           }
           if (!p.b_mn) {
-            tma_load_2d(b, &tmB, &full[stage], k0, n0);  // box (64 k, BN n)
+            tma_load_2d_2cta(b, &tmB, &full[stage], k0, n0);  // box (64 k, 128 n)
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(b + i * 8192, &tmB, &full[stage], n0 + i * 64, k0);
+            for (int i = 0; i < BN / 128; ++i)
+              tma_load_2d_2cta(b + i * 8192, &tmB, &full[stage], n0 + i * 64, k0);
           }
+          if (cta != 0) mbar_arrive_remote(&full[stage], 0);   // "my loads are in flight" -> leader's full barrier
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && cta == 0) {
     // ===================== MMA issuer =====================
     // The whole warp runs this loop with warp-uniform values (descriptors stay in uniform registers); only the
     // tcgen05.mma / tcgen05.commit instructions themselves are issued by one lane.
-    const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    const uint32_t idesc = umma_idesc_bf16(256, BN, p.a_mn, p.b_mn);   // M = 256 across the CTA pair
     // K-major: 8-row groups 1024 B apart; UMMA_K=16 -> +32 B.  MN-major: next 64-wide atom 8192 B
     // away (LBO), 8 k-row groups 1024 B apart (SBO); UMMA_K=16 -> +16 rows = 2048 B.
     const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
@@ -149,7 +153,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
       const int split = t % p.k_splits;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -164,13 +168,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_f16_ss(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+            umma_f16_ss_2cta(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit_2cta(&empty[stage]);  // frees the smem slot in both CTAs once these MMAs retire
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(&acc_full[acc]);   // accumulator ready for the epilogue
+      if (elect_one()) umma_commit_2cta(&acc_full[acc]);   // accumulator ready for both CTAs' epilogues
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -182,9 +186,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int kChunksPerHalf = BN / 64;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
       const int mn = t / p.k_splits;
-      const int m0 = (mn / p.n_tiles) * BM;
+      const int m0 = (mn / p.n_tiles) * 256 + cta * BM;
       const int n0 = (mn % p.n_tiles) * BN;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
@@ -309,32 +313,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync();   // the peer may still be reading TMEM written by the leader's MMAs / smem being multicast-signalled
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN>
-static int launch_gemm(const simvgb_gemm_args* a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+
+// Host launch.  Returns 1 if the shape is not eligible (caller falls back to the 1-CTA kernel).
+int launch_gemm_2cta(const simvgb_gemm_args* a, cudaStream_t stream) {
+  constexpr int BN = 256;
   CUtensorMap tmA, tmB;
   {
-    // A: K-major -> dims (K, M), box (64, 128).  MN-major -> dims (M, K), box (64, 64).
     uint64_t dims[2], strides[1];
     uint32_t box[2];
     if (!a->a_mn_major) { dims[0] = a->K; dims[1] = a->M; box[0] = BK; box[1] = BM; }
     else                { dims[0] = a->M; dims[1] = a->K; box[0] = 64; box[1] = BK; }
     strides[0] = (uint64_t)a->lda * 2;
     if (make_tmap(&tmA, a->A, 2, 2, dims, strides, box, 1)) return -1;
-    if (!a->b_mn_major) { dims[0] = a->K; dims[1] = a->N; box[0] = BK; box[1] = BN; }
+    if (!a->b_mn_major) { dims[0] = a->K; dims[1] = a->N; box[0] = BK; box[1] = BN / 2; }
     else                { dims[0] = a->N; dims[1] = a->K; box[0] = 64; box[1] = BK; }
     strides[0] = (uint64_t)a->ldb * 2;
     if (make_tmap(&tmB, a->B, 2, 2, dims, strides, box, 1)) return -1;
@@ -342,13 +347,13 @@ static int launch_gemm(const simvgb_gemm_args* a, cudaStream_t stream) {
   GemmParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.a_mn = a->a_mn_major; p.b_mn = a->b_mn_major;
-  p.m_tiles = (a->M + BM - 1) / BM;
+  p.m_tiles = (a->M + 255) / 256;
   p.n_tiles = (a->N + BN - 1) / BN;
   p.kb_total = (a->K + BK - 1) / BK;
   int ks = a->k_splits < 1 ? 1 : a->k_splits;
   if (ks > p.kb_total) ks = p.kb_total;
   p.kb_per_split = (p.kb_total + ks - 1) / ks;
-  p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.epilogue = a->epilogue;
   p.bias = a->bias;
   p.out_bf16 = reinterpret_cast<bf16*>(a->out_bf16);
@@ -361,49 +366,17 @@ static int launch_gemm(const simvgb_gemm_args* a, cudaStream_t stream) {
   p.row_scale = a->row_scale;
   p.rows_per_scale = a->rows_per_scale > 0 ? a->rows_per_scale : 1;
   p.accumulate = a->accumulate;
-
   static bool attr_set = false;
   if (!attr_set) {
-    SIMVGB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::kSmemBytes));
+    SIMVGB_CUDA(cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::kSmemBytes));
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
-  int grid = sm_count();
-  if (grid > total) grid = total;
-  gemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  int clusters = sm_count() / 2;
+  if (clusters > total) clusters = total;
+  gemm2_kernel<<<2 * clusters, kThreads, Gemm2Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   SIMVGB_CUDA(cudaGetLastError());
   return 0;
 }
 
 }  // namespace simvgb
-
-namespace simvgb {
-int launch_gemm_2cta(const simvgb_gemm_args* a, cudaStream_t stream);
-}
-
-extern "C" int simvgb_gemm(const simvgb_gemm_args* a, void* stream) {
-  using namespace simvgb;
-  SIMVGB_CHECK(a != nullptr, "simvgb_gemm: null args");
-  SIMVGB_CHECK(a->M > 0 && a->N > 0 && a->K > 0, "simvgb_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
-  SIMVGB_CHECK(a->A && a->B, "simvgb_gemm: null operand");
-  SIMVGB_CHECK((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
-               "simvgb_gemm: operands must be 16-byte aligned");
-  SIMVGB_CHECK(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "simvgb_gemm: bias must be 16-byte aligned");
-  SIMVGB_CHECK((a->lda % 8) == 0 && (a->ldb % 8) == 0, "simvgb_gemm: lda/ldb must be multiples of 8 (TMA 16-byte strides)");
-  SIMVGB_CHECK(a->epilogue >= 0 && a->epilogue <= SIMVGB_EPI_ATOMIC, "simvgb_gemm: bad epilogue %d", a->epilogue);
-  SIMVGB_CHECK(a->k_splits <= 1 || a->epilogue == SIMVGB_EPI_ATOMIC, "simvgb_gemm: k_splits > 1 needs the atomic epilogue");
-  switch (a->epilogue) {
-    case SIMVGB_EPI_BF16: SIMVGB_CHECK(a->out_bf16, "simvgb_gemm: out_bf16 is null"); break;
-    case SIMVGB_EPI_GELU: SIMVGB_CHECK(a->out_bf16 && a->out2_bf16, "simvgb_gemm: GELU needs out_bf16 and out2_bf16"); break;
-    case SIMVGB_EPI_RESID: SIMVGB_CHECK(a->out_f32 && a->res_f32, "simvgb_gemm: RESID needs out_f32 and res_f32"); break;
-    default: SIMVGB_CHECK(a->out_f32, "simvgb_gemm: out_f32 is null"); break;
-  }
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  // Large problems: 2-CTA (cta_group::2) 256x256 tiles.  SIMVGB_GEMM_2CTA=0 forces the 1-CTA kernel (A/B testing).
-  static const int use_2cta = [] { const char* e = getenv("SIMVGB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
-  if (use_2cta && a->N > 128 && a->M >= 256) return launch_gemm_2cta(a, s);
-  // BN=256 tiles unless N is small (head projections, N<=128) where half the tile would be masked.
-  if (a->N > 128) return launch_gemm<256>(a, s);
-  return launch_gemm<128>(a, s);
-}
