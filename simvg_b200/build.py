@@ -13,13 +13,15 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libsimvg_b200.so")
-OBJ = os.path.join(HERE, "build")
+# Tuning builds (tools/*_ab.py): SIMVGB_EXTRA_FLAGS="-DFOO=1" SIMVGB_OUT=simvg_b200/libsimvg_b200_foo.so python -m simvg_b200.build
+EXTRA = os.environ.get("SIMVGB_EXTRA_FLAGS", "").split()
+OUT = os.path.abspath(os.environ.get("SIMVGB_OUT") or os.path.join(HERE, "libsimvg_b200.so"))
+OBJ = os.path.join(HERE, "build" if not EXTRA else "build_" + hashlib.sha256(" ".join(EXTRA).encode()).hexdigest()[:10])
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-]
+] + EXTRA
 
 
 def sources():

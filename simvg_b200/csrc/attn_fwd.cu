@@ -10,8 +10,11 @@
 // thread owns one query row x 64 key columns (row max exchanged through smem) so every SM sub-partition always has
 // several softmax warps to switch between while MUFU / TMEM loads are in flight.
 //   S = Q K_j^T   : tcgen05.mma M=128 N=128 K=64, both operands K-major, S in TMEM columns [0,128)
-//   O += P V_j    : P (bf16) written by the softmax threads into 128B-swizzled smem, V_j read MN-major straight
-//                   from its token-major TMA tile; O in TMEM columns [128,192)
+//   O += P V_j    : P (bf16 pairs packed in 32-bit TMEM columns [192,256)) is written by the softmax threads with
+//                   tcgen05.st and consumed as the A operand straight from TMEM (shared memory only feeds B: at
+//                   head_dim 64 the kernel is bound by shared-memory bandwidth, and P through smem cost 64 KB of the
+//                   144 KB moved per tile); V_j read MN-major straight from its token-major TMA tile; O in TMEM
+//                   columns [128,192)
 // Online softmax with lazy rescaling (O is only rescaled when a row max grows by more than 2^8).
 #include <stdlib.h>
 
@@ -28,11 +31,13 @@ namespace simvgb {
 
 static long long* g_fwd_trace = nullptr;
 
+#ifndef SIMVGB_FWD_POLY
+#define SIMVGB_FWD_POLY 0   // exponentials per group of 4 evaluated on the FMA pipe instead of MUFU (0, 1 or 2)
+#endif
 constexpr int kFwdThreads = 320;
 constexpr int kSoftmaxThreads = 256;
-constexpr int kSlots = 3;  // staging tiles: K double-buffered (slots 0,1: K_{j+1} is prefetched a full tile ahead), V single (slot 2:
-                           // its load hides behind the softmax of the same tile)
-constexpr int kFwdSmem = kTileBytes /*Q*/ + 2 * kTileBytes /*P*/ + kSlots * kTileBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*row-max exchange*/;
+constexpr int kSlots = 4;  // staging tiles: K double-buffered (slots 0,1), V double-buffered (slots 2,3); both prefetched a tile ahead
+constexpr int kFwdSmem = kTileBytes /*Q*/ + kSlots * kTileBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*row-max exchange*/;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnFwdParams {
@@ -55,11 +60,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sP = smem + kTileBytes;
-  uint8_t* sKV = smem + 3 * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (3 + kSlots) * kTileBytes);
+  uint8_t* sKV = smem + kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + kSlots) * kTileBytes);
   uint64_t* q_full = bars;
-  uint64_t* slot_full = bars + 1;             // [kSlots]  0,1 = K ring, 2 = V
+  uint64_t* slot_full = bars + 1;             // [kSlots]  0,1 = K ring, 2,3 = V ring
   uint64_t* slot_empty = bars + 1 + kSlots;   // [kSlots]
   uint64_t* s_full = bars + 1 + 2 * kSlots;
   uint64_t* s_empty = s_full + 1;
@@ -67,7 +71,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   uint64_t* pv_done = s_full + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
   uint32_t* masks = tmem_slot + 2;            // [2][4] validity bits of the (at most two) partial tiles
-  float* xchg = reinterpret_cast<float*>(smem + (3 + kSlots) * kTileBytes + 256);  // [2 parity][2 halves][128 rows]
+  float* xchg = reinterpret_cast<float*>(smem + (1 + kSlots) * kTileBytes + 256);  // [2 parity][2 halves][128 rows]
 
   const AttnGeom& g = p.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,7 +82,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   {
     uint4* z = reinterpret_cast<uint4*>(smem);
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < (3 + kSlots) * kTileBytes / 16; i += kFwdThreads) z[i] = zero;
+    for (int i = threadIdx.x; i < (1 + kSlots) * kTileBytes / 16; i += kFwdThreads) z[i] = zero;
   }
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -103,7 +107,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (uniform registers for UTCHMMA)
-  const uint32_t tmS = tmem, tmO = tmem + 128;
+  const uint32_t tmS = tmem, tmO = tmem + 128, tmP = tmem + 192;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -114,18 +118,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
         mbar_wait(&slot_empty[slot], ((j >> 1) & 1) ^ 1);       // freed when S_{j-2} retired
         load_virtual_tile(sKV + slot * kTileBytes, &slot_full[slot], g, &map_full, &map_tail, &map_text, j, colk, b);
       };
+      auto load_v = [&](int j) {
+        const int slot = 2 + (j & 1);
+        mbar_wait(&slot_empty[slot], ((j >> 1) & 1) ^ 1);       // freed when P V_{j-2} retired
+        load_virtual_tile(sKV + slot * kTileBytes, &slot_full[slot], g, &map_full, &map_tail, &map_text, j, colv, b);
+      };
       load_k(0);
       for (int j = 0; j < nk; ++j) {
         if (j + 1 < nk) load_k(j + 1);
-        mbar_wait(&slot_empty[2], (j & 1) ^ 1);                 // freed when P V_{j-1} retired
-        load_virtual_tile(sKV + 2 * kTileBytes, &slot_full[2], g, &map_full, &map_tail, &map_text, j, colv, b);
+        load_v(j);
       }
     }
   } else if (warp == 1) {
     // MMA issuer: warp-uniform control flow, single-lane issue (keeps descriptors in uniform registers).
     const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     const uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);  // A = P (K-major), B = V (MN-major)
-    const uint64_t dQ = umma_smem_desc(smem_u32(sQ), 16, 1024), dP = umma_smem_desc(smem_u32(sP), 16, 1024);
+    const uint64_t dQ = umma_smem_desc(smem_u32(sQ), 16, 1024);
     const uint64_t dKV_k = umma_smem_desc(smem_u32(sKV), 16, 1024), dKV_mn = umma_smem_desc(smem_u32(sKV), 8192, 1024);
     auto issue_s = [&](int j) {
       const int slot = j & 1;
@@ -149,18 +157,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
       if (trace) p.ts[j * 8 + 1] = clock64();
       if (j + 1 < nk) issue_s(j + 1);
       if (trace) p.ts[j * 8 + 2] = clock64();
-      const int slot = 2;
+      const int slot = 2 + (j & 1);
       mbar_wait(p_full, j & 1);
       if (trace) p.ts[j * 8 + 3] = clock64();
-      mbar_wait(&slot_full[slot], j & 1);
+      mbar_wait(&slot_full[slot], (j >> 1) & 1);
       if (trace) p.ts[j * 8 + 4] = clock64();
       tc_fence_after();
       const uint64_t dv = dKV_mn + slot * (kTileBytes >> 4);
       if (elect_one()) {
         if (!(SIMVGB_DBG(p) & 8))
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k)
-          umma_f16_ss(tmO, dP + (k >> 2) * (kTileBytes >> 4) + (k & 3) * 2, dv + k * 128, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < kTile / 16; ++k)   // A = P[:, 16k .. 16k+16) = 8 packed TMEM columns
+          umma_f16_ts(tmO, tmP + 8 * k, dv + k * 128, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&slot_empty[slot]);
         umma_commit(pv_done);
       }
@@ -226,34 +234,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
           tmem_wait_st();
         }
       }
+      // exp2 and bf16 packing fused (in place: pair i of va/vb lands in word i), so no fp32 probability outlives its pair
       float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float pa = (SIMVGB_DBG(p) & 2) ? __uint_as_float(va[i]) : ex2_approx(fmaf(__uint_as_float(va[i]), kLog2e, -m_use));
-        const float pb = (SIMVGB_DBG(p) & 2) ? __uint_as_float(vb[i]) : ex2_approx(fmaf(__uint_as_float(vb[i]), kLog2e, -m_use));
-        sum += pa + pb;
-        va[i] = __float_as_uint(pa);
-        vb[i] = __float_as_uint(pb);
+      for (int i = 0; i < 16; ++i) {
+        float a0, a1, b0, b1;
+        if (SIMVGB_DBG(p) & 2) {
+          a0 = __uint_as_float(va[2 * i]); a1 = __uint_as_float(va[2 * i + 1]);
+          b0 = __uint_as_float(vb[2 * i]); b1 = __uint_as_float(vb[2 * i + 1]);
+        } else {
+          a0 = ex2_approx(fmaf(__uint_as_float(va[2 * i]), kLog2e, -m_use));
+          a1 = ex2_approx(fmaf(__uint_as_float(va[2 * i + 1]), kLog2e, -m_use));
+#if SIMVGB_FWD_POLY >= 2
+          const float xb0 = fmaf(__uint_as_float(vb[2 * i]), kLog2e, -m_use);
+          b0 = partial ? ex2_approx(xb0) : ex2_fma(fmaxf(xb0, -100.f));
+#else
+          b0 = ex2_approx(fmaf(__uint_as_float(vb[2 * i]), kLog2e, -m_use));
+#endif
+#if SIMVGB_FWD_POLY >= 1
+          // full tiles only (warp-uniform): masked scores are -inf, which the FMA-pipe exp2 does not handle
+          const float xb1 = fmaf(__uint_as_float(vb[2 * i + 1]), kLog2e, -m_use);
+          b1 = partial ? ex2_approx(xb1) : ex2_fma(fmaxf(xb1, -100.f));
+#else
+          b1 = ex2_approx(fmaf(__uint_as_float(vb[2 * i + 1]), kLog2e, -m_use));
+#endif
+        }
+        sum += (a0 + a1) + (b0 + b1);
+        va[i] = pack_bf16x2(a0, a1);   // TMEM column c of P holds keys 2c (low half), 2c+1 (high half)
+        vb[i] = pack_bf16x2(b0, b1);
       }
-      const uint32_t aP = smem_u32(sP);
-      if (!(SIMVGB_DBG(p) & 4))
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        st_shared_v4(aP + swz_off(r, half * 8 + q4),
-                     pack_bf16x2(__uint_as_float(va[8 * q4]), __uint_as_float(va[8 * q4 + 1])),
-                     pack_bf16x2(__uint_as_float(va[8 * q4 + 2]), __uint_as_float(va[8 * q4 + 3])),
-                     pack_bf16x2(__uint_as_float(va[8 * q4 + 4]), __uint_as_float(va[8 * q4 + 5])),
-                     pack_bf16x2(__uint_as_float(va[8 * q4 + 6]), __uint_as_float(va[8 * q4 + 7])));
-        st_shared_v4(aP + swz_off(r, half * 8 + 4 + q4),
-                     pack_bf16x2(__uint_as_float(vb[8 * q4]), __uint_as_float(vb[8 * q4 + 1])),
-                     pack_bf16x2(__uint_as_float(vb[8 * q4 + 2]), __uint_as_float(vb[8 * q4 + 3])),
-                     pack_bf16x2(__uint_as_float(vb[8 * q4 + 4]), __uint_as_float(vb[8 * q4 + 5])),
-                     pack_bf16x2(__uint_as_float(vb[8 * q4 + 6]), __uint_as_float(vb[8 * q4 + 7])));
+      if (!(SIMVGB_DBG(p) & 4)) {
+        tmem_st16x2(tmP + lane_base + half * 32, va, vb);
+        tmem_wait_st();
       }
       l = l * alpha + sum;
       m = m_use;
-      tc_fence_before();
-      fence_proxy_async();   // P stores (generic proxy) -> visible to tcgen05.mma (async proxy)
+      tc_fence_before();     // P is in TMEM (tcgen05.st completed above): order it before the MMA warp's tcgen05.mma
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }

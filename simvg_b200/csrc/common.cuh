@@ -196,6 +196,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[30]), "r"(v[31])
       : "memory");
 }
+// 32 lanes x 32 consecutive columns taken from the first 16 words of two register arrays (lo -> columns 0-15, hi -> 16-31)
+__device__ __forceinline__ void tmem_st16x2(uint32_t taddr, const uint32_t (&lo)[32], const uint32_t (&hi)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]),
+      "r"(lo[8]), "r"(lo[9]), "r"(lo[10]), "r"(lo[11]), "r"(lo[12]), "r"(lo[13]), "r"(lo[14]), "r"(lo[15]),
+      "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]),
+      "r"(hi[8]), "r"(hi[9]), "r"(hi[10]), "r"(hi[11]), "r"(hi[12]), "r"(hi[13]), "r"(hi[14]), "r"(hi[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -293,6 +305,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// 2^x on the FMA pipe (no MUFU): Cody-Waite split x = n + f with a round-down add against 1.5*2^23, cubic minimax for
+// 2^f on [0,1) (max rel err ~1e-4, below bf16 rounding of the result), exponent patched in with integer ops.  Used to
+// take part of the softmax exponentials off the 16-op/clk/SM MUFU unit, which bounds attention at head_dim 64.
+// Requires finite x >= -126 (callers pass x <= ~8).
+__device__ __forceinline__ float ex2_fma(float x) {
+  float r;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(12582912.0f));   // low mantissa bits = floor(x)
+  const float f = x - (r - 12582912.0f);
+  float p = fmaf(0.077119089663028717f, f, 0.227564394474029541f);
+  p = fmaf(p, f, 0.695146143436431885f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
 }
 
 // erf via Abramowitz & Stegun 7.1.28:  erf(x) = 1 - (1 + a1 x + ... + a6 x^6)^-16  (x >= 0, |abs err| <= 3e-7, i.e.
