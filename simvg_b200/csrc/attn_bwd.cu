@@ -4,15 +4,24 @@
 // (/root/reference/simvg/models/vis_encs/beit/beit3_base.py:137-145; driven by loss.backward() at
 // /root/reference/simvg/apis/train.py:80).
 //
-// One CTA owns one 128-key tile j of one (b, h) and loops over the query tiles i:
-//     S  = Q_i K_j^T                 P  = exp2(S*log2e - LSE_i)      (masked keys / rows -> 0)
-//     dP = dO_i V_j^T                dS = P o (dP - delta_i)
-//     dV_j += P^T dO_i               dK_j += dS^T Q_i                 dQ_i += dS K_j   (fp32 red.global.add)
-// All five products are tcgen05.mma with accumulators in TMEM (S, dP: 128 columns each; dV, dK, dQ: 64 each).
-// P and dS are written once to 128B-swizzled smem by the compute threads and consumed twice: K-major (dQ = dS K)
-// and MN-major (P^T dO, dS^T Q) — the same bytes, two descriptors — so nothing is transposed.
-// Warp roles: 0 TMA producer, 1 MMA issuer, 2-9 compute (two warps per TMEM lane quarter, 64 key columns each — two
-// resident warps per SM sub-partition hide each other's MUFU/TMEM latency), 10-13 dQ write-back.
+// One CTA owns one 128-key tile j of one (b, h) and loops over the query tiles i.  Scores are computed TRANSPOSED
+// (keys on the TMEM lanes, queries along the columns) so that P^T and dS^T can feed the dV / dK products straight from
+// tensor memory as the A operand — at head_dim 64 the kernel is bound by shared-memory bandwidth (every SS-form
+// tcgen05.mma streams both operands from smem), and this removes P entirely and half of dS from shared memory:
+//     S^T  = K_j Q_i^T - LSE_i[q]/log2e      P^T  = exp2(S^T*log2e)      (masked keys -> 0; non-token queries: LSE -> huge)
+//     dP^T = V_j dO_i^T - delta_i[q]         dS^T = P^T o dP^T
+// The per-query statistics are per-COLUMN constants in this orientation; rather than have every compute thread fetch
+// them (one shared-memory wavefront per value per warp — more traffic than the operands), they are folded into the
+// accumulators by one extra K=16 tcgen05.mma each:  ones[keys,16] x stat[q,16]^T with the statistic split into three bf16
+// terms (hi + mid + lo, exact to fp32 rounding) in columns 0-2 of a 32-byte K-slot written by the producer warp.
+//     dV_j += P^T dO_i    (A = P^T  from TMEM)
+//     dK_j += dS^T Q_i    (A = dS^T from TMEM, written in place over dP^T)
+//     dQ_i  = dS K_j      (A = dS^T tile in smem read MN-major, B = K_j MN-major; fp32 red.global.add)
+// TMEM columns: S^T [0,128)  dP^T/dS^T [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)  P^T (bf16 pairs) [448,512).
+// Tensor-pipe order per pair: S(i+1), dK(i), dP(i+1), dV(i), dQ(i) — in-order execution makes the in-place dS^T -> dP^T
+// hand-over safe without a round trip through the issuing warp.
+// Warp roles: 0 TMA producer (Q_i, dO_i ring) + statistic K-slots, 1 MMA issuer, 2-17 compute (four warps per TMEM lane
+// quarter, 32 query columns each), 18-21 dQ write-back.
 #include <stdlib.h>
 
 #include "attn_common.cuh"
@@ -31,12 +40,23 @@ int make_attn_maps(CUtensorMap* full, CUtensorMap* tail, CUtensorMap* text, cons
 
 constexpr int kBwdThreads = 704;        // TMA + MMA + 16 compute + 4 dQ warps
 constexpr int kComputeThreads = 512;    // four warps per TMEM lane quarter, one 32-column chunk each
-#ifndef SIMVGB_BWD_STAGES
-#define SIMVGB_BWD_STAGES 2
+#ifndef SIMVGB_BWD_POLY
+#define SIMVGB_BWD_POLY 0
 #endif
-constexpr int kQS = SIMVGB_BWD_STAGES;   // Q_i / dO_i ring depth (TMA latency is ~1.5 us: 2 stages cannot hide it)
-constexpr int kBwdTiles = 2 + 2 * kQS + 8;   // K, V, Q[kQS], dO[kQS], P[2](2 sub-tiles), dS[2](2 sub-tiles)
-constexpr int kBwdSmem = kBwdTiles * kTileBytes + 1024 + 256;
+#ifndef SIMVGB_BWD_DQ_PAIR
+#define SIMVGB_BWD_DQ_PAIR 1   // lane pairs exchange halves of their dQ rows so each red.v4 pair covers a 32-byte sector
+#endif
+#ifndef SIMVGB_BWD_STAGES
+#define SIMVGB_BWD_STAGES 3
+#endif
+constexpr int kQS = SIMVGB_BWD_STAGES;   // Q_i / dO_i / LSE_i / delta_i ring depth (TMA latency is ~1.5 us)
+constexpr int kStatSlots = 2 * kQS + 1;                  // 32-byte K-slots: (LSE, delta) per stage + one all-ones A slot
+constexpr int kStatTiles = (kStatSlots + 3) / 4;         // four K-slots per 128B-swizzled [128 x 64] tile
+constexpr int kBwdTiles = 2 + 2 * kQS + 4 + kStatTiles;  // K, V, Q[kQS], dO[kQS], dS^T[2 buffers](2 sub-tiles), statistic slots
+constexpr int kStageBytes = 2 * 2 * kTile * 4;           // raw LSE_i / delta_i rows (bulk-copied, 2 deep), converted into K-slots by warp 0
+// 14 tiles + staging + barriers = 231,680 B of the 232,448 B a CTA may own: no slack for manual alignment, so the dynamic
+// shared-memory window itself must be 1024-byte aligned (it is when the kernel has no static __shared__; checked at entry).
+constexpr int kBwdSmem = kBwdTiles * kTileBytes + kStageBytes + 256;
 constexpr float kLog2eB = 1.4426950408889634f;
 
 struct AttnBwdParams {
@@ -61,29 +81,40 @@ struct AttnMaps6 {
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes: multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();         // 128B-swizzled TMA / UMMA tiles need 1024-byte alignment
   uint8_t* sK = smem;
   uint8_t* sV = smem + kTileBytes;
   uint8_t* sQ = smem + 2 * kTileBytes;                 // [kQS]
   uint8_t* sdO = smem + (2 + kQS) * kTileBytes;        // [kQS]
-  uint8_t* sP = smem + (2 + 2 * kQS) * kTileBytes;     // [2 buffers][2 sub-tiles]
-  uint8_t* sdS = smem + (6 + 2 * kQS) * kTileBytes;    // [2 buffers][2 sub-tiles]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdTiles * kTileBytes);
+  uint8_t* sdS = smem + (2 + 2 * kQS) * kTileBytes;    // [2 buffers][2 sub-tiles]: rows = keys, 128 queries per row
+  uint8_t* sStat = smem + (6 + 2 * kQS) * kTileBytes;  // K-slot n: rows 128 B apart, 16-byte chunks 2n', 2n'+1 (n' = n % 4) of tile n / 4
+  float* sStage = reinterpret_cast<float*>(smem + kBwdTiles * kTileBytes);   // [2][2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdTiles * kTileBytes + kStageBytes);
   uint64_t* kv_full = bars;
   uint64_t* qdo_full = bars + 1;           // [kQS]
   uint64_t* qdo_empty = bars + 1 + kQS;    // [kQS]
-  uint64_t* s_full = bars + 1 + 2 * kQS;
-  uint64_t* s_empty = s_full + 1;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* pds_done = s_full + 3;   // [2]: one per P/dS buffer — a single barrier could advance two phases past a slow
-                                     // waiter (parity aliasing) once the buffers are double-buffered
-  uint64_t* dq_full = s_full + 5;
-  uint64_t* dq_empty = s_full + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 7);
+  uint64_t* s_full = bars + 1 + 2 * kQS;   // S^T(i) complete
+  uint64_t* dp_full = s_full + 1;          // dP^T(i) complete
+  uint64_t* s_empty = s_full + 2;          // every compute warp has S^T(i) in registers
+  uint64_t* p_full = s_full + 3;           // P^T(i), dS^T(i) (TMEM) and dS^T(i) (smem) written
+  uint64_t* pt_free = s_full + 4;          // dV(i) has consumed P^T(i)
+  uint64_t* ds_free = s_full + 5;          // [2]: dQ(i) has consumed smem dS^T buffer i & 1
+  uint64_t* dq_full = s_full + 7;
+  uint64_t* dq_empty = s_full + 8;
+  uint64_t* mma_done = s_full + 9;
+  uint64_t* st_full = s_full + 10;         // [2]: raw statistics have landed in the staging buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 12);
   uint32_t* kmask = tmem_slot + 2;  // [4]
 
   const AttnGeom& g = p.g;
@@ -95,18 +126,23 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
   {
     uint4* z = reinterpret_cast<uint4*>(smem);
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < kBwdTiles * kTileBytes / 16; i += kBwdThreads) z[i] = zero;
+    for (int i = threadIdx.x; i < kBwdTiles * kTileBytes / 16; i += kBwdThreads) z[i] = zero;   // staging tiles, statistic slots
   }
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 2);   // K_j and V_j arrive separately
-    for (int s = 0; s < kQS; ++s) { mbar_init(&qdo_full[s], 2); mbar_init(&qdo_empty[s], 1); }  // Q_i + dO_i
+    for (int s = 0; s < kQS; ++s) { mbar_init(&qdo_full[s], 3); mbar_init(&qdo_empty[s], 1); }  // Q_i + dO_i + stats
     mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
     mbar_init(s_empty, kComputeThreads / 32);   // one elected arrival per compute warp
     mbar_init(p_full, kComputeThreads / 32);
-    mbar_init(&pds_done[0], 1);
-    mbar_init(&pds_done[1], 1);
+    mbar_init(pt_free, 1);
+    mbar_init(&ds_free[0], 1);
+    mbar_init(&ds_free[1], 1);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 4);
+    mbar_init(mma_done, 1);
+    mbar_init(&st_full[0], 1);
+    mbar_init(&st_full[1], 1);
     fence_barrier_init();
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {   // warps 2-5
@@ -122,181 +158,243 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (uniform registers for UTCHMMA)
-  const uint32_t tmS = tmem, tmdP = tmem + 128, tmdV = tmem + 256, tmdK = tmem + 320, tmdQ = tmem + 384;
+  const uint32_t tmS = tmem, tmdP = tmem + 128, tmdV = tmem + 256, tmdK = tmem + 320, tmdQ = tmem + 384, tmP = tmem + 448;
 
   if (warp == 0) {
+    const int colq = h * kHeadDim, colk = g.D + h * kHeadDim, colv = 2 * g.D + h * kHeadDim;
+    const float* lse = p.lse + ((long long)b * g.H + h) * lse_stride;
+    const float* delta = p.delta + ((long long)b * g.H + h) * lse_stride;
+    // Writes 16 bf16 (K elements 0..15 of K-slot `slot`) of row `row`: {hi, mid, lo, 0 ...} with hi + mid + lo == v to fp32 rounding.
+    auto put_stat = [&](int slot, int row, float v) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const float r1 = v - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+      const uint32_t w0 = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16);
+      const uint32_t w1 = (uint32_t)__bfloat16_as_ushort(lo);
+      const uint32_t base = smem_u32(sStat) + (slot >> 2) * kTileBytes + row * 128;
+      const int c0 = 2 * (slot & 3);
+      st_shared_v4(base + (((c0) ^ (row & 7)) << 4), w0, w1, 0u, 0u);
+      st_shared_v4(base + (((c0 + 1) ^ (row & 7)) << 4), 0u, 0u, 0u, 0u);
+    };
+    // all-ones A slot (every key row contributes 1 x statistic)
+    for (int row = lane; row < kTile; row += 32) {
+      const uint32_t base = smem_u32(sStat) + ((2 * kQS) >> 2) * kTileBytes + row * 128;
+      const int c0 = 2 * ((2 * kQS) & 3);
+      st_shared_v4(base + (((c0) ^ (row & 7)) << 4), 0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+      st_shared_v4(base + (((c0 + 1) ^ (row & 7)) << 4), 0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    }
+    // K_j and V_j share one barrier (two expect_tx arrivals, init count 2); Q_i, dO_i and the statistic slots share one (3).
+    // The raw LSE / delta rows are bulk-copied (TMA path: plain global loads from this warp would queue behind the dQ
+    // reductions in the LSU) into a 2-deep staging ring one iteration before they are converted into K-slots.
+    auto convert_stats = [&](int i) {
+      const int s = i % kQS;
+      mbar_wait(&st_full[i & 1], (i >> 1) & 1);
+      const float* raw = sStage + (i & 1) * 2 * kTile;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int row = lane + 32 * t, qv = i * kTile + row;
+        const bool ok = (qv < g.Lv) || (qv >= g.T0 && qv < g.T0 + g.Lt);
+        put_stat(2 * s, row, ok ? -raw[row] * 0.6931471805599453f : -60000.f);   // natural-log units: exp2((s + v) * log2e)
+        put_stat(2 * s + 1, row, ok ? -raw[kTile + row] : 0.f);
+      }
+      fence_proxy_async();   // statistic slots (generic proxy) -> tcgen05.mma (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&qdo_full[s]);
+    };
+    auto load_stats = [&](int i) {   // staging buffer i & 1 was drained by convert_stats(i - 2) (program order + its proxy fence)
+      mbar_expect_tx(&st_full[i & 1], 2 * kTile * 4);
+      bulk_load(sStage + (i & 1) * 2 * kTile, lse + i * kTile, kTile * 4, &st_full[i & 1]);
+      bulk_load(sStage + (i & 1) * 2 * kTile + kTile, delta + i * kTile, kTile * 4, &st_full[i & 1]);
+    };
     if (lane == 0) {
-      const int colq = h * kHeadDim, colk = g.D + h * kHeadDim, colv = 2 * g.D + h * kHeadDim;
-      // K_j and V_j share one barrier (two expect_tx arrivals, init count 2); likewise Q_i and dO_i.
       load_virtual_tile(sK, kv_full, g, &maps.qkv_full, &maps.qkv_tail, &maps.qkv_text, kt, colk, b);
-      for (int i = 0; i < nq; ++i) {
-        const int s = i % kQS;
-        mbar_wait(&qdo_empty[s], ((i / kQS) & 1) ^ 1);
+      load_stats(0);
+    }
+    for (int i = 0; i < nq; ++i) {
+      const int s = i % kQS;
+      if (lane == 0 && i + 1 < nq) load_stats(i + 1);   // a full iteration ahead of its conversion
+      mbar_wait(&qdo_empty[s], ((i / kQS) & 1) ^ 1);
+      if (lane == 0) {
         load_virtual_tile(sQ + s * kTileBytes, &qdo_full[s], g, &maps.qkv_full, &maps.qkv_tail, &maps.qkv_text, i,
                           colq, b);
         if (i == 0) load_virtual_tile(sV, kv_full, g, &maps.qkv_full, &maps.qkv_tail, &maps.qkv_text, kt, colv, b);
         load_virtual_tile(sdO + s * kTileBytes, &qdo_full[s], g, &maps.do_full, &maps.do_tail, &maps.do_text, i,
                           h * kHeadDim, b);
       }
+      __syncwarp();
+      convert_stats(i);   // raw rows landed long ago; the K-slots of stage s are free (qdo_empty above)
     }
   } else if (warp == 1) {
     // MMA issuer: warp-uniform control flow, single-lane issue (keeps descriptors in uniform registers).
-    const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-    const uint32_t idesc_dq = umma_idesc_bf16(128, kHeadDim, 0, 1);   // A = dS K-major, B = K_j MN-major
-    const uint32_t idesc_dkv = umma_idesc_bf16(128, kHeadDim, 1, 1);  // A = P^T / dS^T MN-major, B = dO / Q MN-major
+    const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);         // S^T / dP^T: A = K_j / V_j, B = Q_i / dO_i, all K-major
+    const uint32_t idesc_ts = umma_idesc_bf16(128, kHeadDim, 0, 1);   // dV / dK: A from TMEM, B = dO_i / Q_i MN-major
+    const uint32_t idesc_dq = umma_idesc_bf16(128, kHeadDim, 1, 1);   // dQ: A = dS^T tile MN-major, B = K_j MN-major
     const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
     const uint64_t dK_kmaj = umma_smem_desc(k_addr, 16, 1024), dV_kmaj = umma_smem_desc(v_addr, 16, 1024);
     const uint64_t dK_mn = umma_smem_desc(k_addr, 8192, 1024);
-    const uint64_t dP_mn0 = umma_smem_desc(smem_u32(sP), kTileBytes, 1024), dS_mn0 = umma_smem_desc(smem_u32(sdS), kTileBytes, 1024);
-    const uint64_t dS_kmaj0 = umma_smem_desc(smem_u32(sdS), 16, 1024);
+    const uint64_t dS_mn0 = umma_smem_desc(smem_u32(sdS), kTileBytes, 1024);
     const uint64_t dQ_kmaj0 = umma_smem_desc(smem_u32(sQ), 16, 1024), dO_kmaj0 = umma_smem_desc(smem_u32(sdO), 16, 1024);
     const uint64_t dQ_mn0 = umma_smem_desc(smem_u32(sQ), 8192, 1024), dO_mn0 = umma_smem_desc(smem_u32(sdO), 8192, 1024);
     constexpr uint32_t kTileStep = kTileBytes >> 4;   // descriptor start-address units per 16 KB tile
-    auto issue_sdp = [&](int i) {
-      const int s = i % kQS;
-      mbar_wait(&qdo_full[s], (i / kQS) & 1);
-      tc_fence_after();
-      const uint64_t dq = dQ_kmaj0 + s * kTileStep, dd = dO_kmaj0 + s * kTileStep;
+    const uint64_t dStat0 = umma_smem_desc(smem_u32(sStat), 16, 1024);
+    auto stat_desc = [&](int slot) { return dStat0 + (slot >> 2) * kTileStep + 2 * (slot & 3); };
+    const uint64_t dOnes = stat_desc(2 * kQS);
+    auto issue_s = [&](int i) {     // S^T(i) = K_j Q_i^T - LSE_i[q] / log2e
+      const uint64_t dq = dQ_kmaj0 + (i % kQS) * kTileStep, dst = stat_desc(2 * (i % kQS));
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(tmS, dq + 2 * k, dK_kmaj + 2 * k, idesc_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(tmdP, dd + 2 * k, dV_kmaj + 2 * k, idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmS, dK_kmaj + 2 * k, dq + 2 * k, idesc_s, k > 0);
+        umma_f16_ss(tmS, dOnes, dst, idesc_s, 1u);
         umma_commit(s_full);
       }
       __syncwarp();
     };
-    mbar_wait(kv_full, 0);
-    issue_sdp(0);
+    auto issue_dp = [&](int i) {    // dP^T(i) = V_j dO_i^T - delta_i[q]
+      const uint64_t dd = dO_kmaj0 + (i % kQS) * kTileStep, dst = stat_desc(2 * (i % kQS) + 1);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmdP, dV_kmaj + 2 * k, dd + 2 * k, idesc_s, k > 0);
+        umma_f16_ss(tmdP, dOnes, dst, idesc_s, 1u);
+        umma_commit(dp_full);
+      }
+      __syncwarp();
+    };
     const bool trace = p.ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+    mbar_wait(kv_full, 0);
+    mbar_wait(&qdo_full[0], 0);
+    tc_fence_after();
+    issue_s(0);
+    issue_dp(0);
     for (int i = 0; i < nq; ++i) {
       const int s = i % kQS;
-      const int pb = i & 1;   // P / dS buffer of this pair
-      mbar_wait(s_empty, i & 1);
+      const int pb = i & 1;   // smem dS^T buffer of this pair
       if (trace) p.ts[i * 16 + 0] = clock64();
-      if (i + 1 < nq) issue_sdp(i + 1);
+      if (i + 1 < nq) {       // S^T(i+1) runs on the tensor pipe while the compute warps work on pair i
+        mbar_wait(&qdo_full[(i + 1) % kQS], ((i + 1) / kQS) & 1);
+        mbar_wait(s_empty, i & 1);
+        tc_fence_after();
+        issue_s(i + 1);
+      }
       if (trace) p.ts[i * 16 + 1] = clock64();
       mbar_wait(p_full, i & 1);
       if (trace) p.ts[i * 16 + 2] = clock64();
-      if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);
-      if (trace) p.ts[i * 16 + 3] = clock64();
       tc_fence_after();
-      const uint64_t dsk = dS_kmaj0 + pb * 2 * kTileStep, dsm = dS_mn0 + pb * 2 * kTileStep, dpm = dP_mn0 + pb * 2 * kTileStep;
       const uint64_t dqm = dQ_mn0 + s * kTileStep, dom = dO_mn0 + s * kTileStep;
       if (!(SIMVGB_DBG(p) & 16) && elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // dQ_i = dS K_j        (A: dS K-major, B: K_j MN-major)
-          umma_f16_ss(tmdQ, dsk + (k >> 2) * kTileStep + (k & 3) * 2, dK_mn + k * 128, idesc_dq, k > 0);
-      }
-      if (elect_one()) umma_commit(dq_full);
-      if (!(SIMVGB_DBG(p) & 16) && elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)   // dV_j += P^T dO_i     (A: P MN-major, B: dO_i MN-major)
-          umma_f16_ss(tmdV, dpm + k * 128, dom + k * 128, idesc_dkv, (i > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)   // dK_j += dS^T Q_i     (A: dS MN-major, B: Q_i MN-major)
-          umma_f16_ss(tmdK, dsm + k * 128, dqm + k * 128, idesc_dkv, (i > 0 || k > 0) ? 1u : 0u);
-      }
-      if (elect_one()) {
-        umma_commit(&qdo_empty[s]);
-        umma_commit(&pds_done[pb]);
+        for (int k = 0; k < 8; ++k)   // dK_j += dS^T Q_i     (A: dS^T in TMEM, 16 packed columns per 32-query chunk)
+          umma_f16_ts(tmdK, tmdP + 32 * (k >> 1) + 8 * (k & 1), dqm + k * 128, idesc_ts, (i > 0 || k > 0) ? 1u : 0u);
       }
       __syncwarp();
+      if (i + 1 < nq) issue_dp(i + 1);   // overwrites dS^T(i): the tensor pipe executes in issue order, after dK(i)
+      if (!(SIMVGB_DBG(p) & 16) && elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dV_j += P^T dO_i     (A: P^T in TMEM)
+          umma_f16_ts(tmdV, tmP + 8 * k, dom + k * 128, idesc_ts, (i > 0 || k > 0) ? 1u : 0u);
+      }
+      if (elect_one()) {
+        umma_commit(pt_free);
+        umma_commit(&qdo_empty[s]);   // S(i), dP(i), dK(i), dV(i) were the readers of this Q_i / dO_i / statistics stage
+      }
+      __syncwarp();
+      if (trace) p.ts[i * 16 + 3] = clock64();
+      if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);
       if (trace) p.ts[i * 16 + 4] = clock64();
+      tc_fence_after();
+      const uint64_t dsm = dS_mn0 + pb * 2 * kTileStep;
+      if (!(SIMVGB_DBG(p) & 16) && elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dQ_i = dS K_j        (A: smem dS^T tile read MN-major, B: K_j MN-major)
+          umma_f16_ss(tmdQ, dsm + k * 128, dK_mn + k * 128, idesc_dq, k > 0);
+      }
+      if (elect_one()) {
+        umma_commit(dq_full);
+        umma_commit(&ds_free[pb]);
+        if (i == nq - 1) umma_commit(mma_done);
+      }
+      __syncwarp();
+      if (trace) p.ts[i * 16 + 5] = clock64();
     }
   } else if (warp < 18) {
-    // ------------------------------ compute: P and dS ------------------------------
+    // ------------------------------ compute: P^T and dS^T ------------------------------
     const int quarter = warp & 3;
-    const int chunk = (warp - 2) >> 2;     // key columns [32*chunk, 32*chunk + 32)
-    const int half = chunk;                // (chunks 0,1 also store dK columns [32*chunk, +32) at the end)
-    const int r = quarter * 32 + lane;
+    const int c = (warp - 2) >> 2;         // query columns [32c, 32c + 32) of the pair
+    const int r = quarter * 32 + lane;     // key row of this thread
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-    const float* lse = p.lse + ((long long)b * g.H + h) * lse_stride;
-    const float* delta = p.delta + ((long long)b * g.H + h) * lse_stride;
     const bool ktile_masked = kt >= g.nfull;
+    const bool kvalid = (kmask[quarter] >> lane) & 1u;
+    const bool trace = p.ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
     for (int i = 0; i < nq; ++i) {
-      const int qv = i * kTile + r;
-      const bool row_ok = (qv < g.Lv) || (qv >= g.T0 && qv < g.T0 + g.Lt);
-      const float L = row_ok ? __ldg(lse + qv) : 0.f;
-      const float dl = row_ok ? __ldg(delta + qv) : 0.f;
-      const bool slow = ktile_masked || (i >= g.nfull);   // warp-uniform: only tail tiles need masking
-      const bool trace = p.ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
       if (trace) p.ts[i * 16 + 8] = clock64();
       mbar_wait(s_full, i & 1);
       if (trace) p.ts[i * 16 + 9] = clock64();
-      if (i > 1) mbar_wait(&pds_done[i & 1], ((i >> 1) + 1) & 1);   // MMAs of pair i-2 have finished reading this buffer
-      if (trace) p.ts[i * 16 + 10] = clock64();
-      const uint32_t aP = smem_u32(sP) + (i & 1) * 2 * kTileBytes;
-      const uint32_t adS = smem_u32(sdS) + (i & 1) * 2 * kTileBytes;
       tc_fence_after();
-      {
-        const int c = chunk;
-        uint32_t sv[32], dv[32];
-        if (!(SIMVGB_DBG(p) & 4)) {
-          tmem_ld32(tmS + lane_base + c * 32, sv);
-          tmem_ld32(tmdP + lane_base + c * 32, dv);
-          tmem_wait_ld();
-          // this warp's share of S / dP is in registers: release it now so S_{i+1} / dP_{i+1} overlap the math below
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_empty);
-        } else {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) { sv[t] = 0; dv[t] = 0; }
-        }
-        float pr[32], ds[32];
-        if (SIMVGB_DBG(p) & 2) {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) { pr[t] = __uint_as_float(sv[t]); ds[t] = __uint_as_float(dv[t]); }
-        } else if (!slow) {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            const float pv = ex2_approx(fmaf(__uint_as_float(sv[t]), kLog2eB, -L));
-            pr[t] = pv;
-            ds[t] = pv * (__uint_as_float(dv[t]) - dl);
-          }
-        } else {
-          const uint32_t bits = row_ok ? kmask[c] : 0u;
-#pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            const float pv = (bits >> t) & 1u ? ex2_approx(fmaf(__uint_as_float(sv[t]), kLog2eB, -L)) : 0.f;
-            pr[t] = pv;
-            ds[t] = pv * (__uint_as_float(dv[t]) - dl);
-          }
-        }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint32_t off = swz_off(r, c * 4 + q4);
-          st_shared_v4(aP + off, pack_bf16x2(pr[8 * q4], pr[8 * q4 + 1]), pack_bf16x2(pr[8 * q4 + 2], pr[8 * q4 + 3]),
-                       pack_bf16x2(pr[8 * q4 + 4], pr[8 * q4 + 5]), pack_bf16x2(pr[8 * q4 + 6], pr[8 * q4 + 7]));
-          st_shared_v4(adS + off, pack_bf16x2(ds[8 * q4], ds[8 * q4 + 1]), pack_bf16x2(ds[8 * q4 + 2], ds[8 * q4 + 3]),
-                       pack_bf16x2(ds[8 * q4 + 4], ds[8 * q4 + 5]), pack_bf16x2(ds[8 * q4 + 6], ds[8 * q4 + 7]));
-        }
-      }
-      if (trace) p.ts[i * 16 + 11] = clock64();
+      uint32_t sv[32];
+      tmem_ld32(tmS + lane_base + c * 32, sv);
+      tmem_wait_ld();
       tc_fence_before();
-      fence_proxy_async();   // this thread's P/dS stores -> async proxy
       __syncwarp();
-      if (lane == 0) {
-        if (SIMVGB_DBG(p) & 4) mbar_arrive(s_empty);
-        mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(s_empty);   // S^T(i) is in registers: S^T(i+1) may overwrite it
+      // P^T as bf16 pairs (TMEM column t of the chunk holds queries 2t, 2t+1).  Only the packed form stays live across the
+      // wait for dP^T: dS^T below uses the bf16-rounded P^T, the value the dV product sees.
+      uint32_t pk[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+#if SIMVGB_BWD_POLY
+        // every other exponential on the FMA pipe (the P phase is otherwise bound by the 16/clk/SM MUFU unit)
+        pk[t] = pack_bf16x2(ex2_approx(__uint_as_float(sv[2 * t]) * kLog2eB),
+                            ex2_fma(fmaxf(__uint_as_float(sv[2 * t + 1]) * kLog2eB, -120.f)));
+#else
+        pk[t] = pack_bf16x2(ex2_approx(__uint_as_float(sv[2 * t]) * kLog2eB), ex2_approx(__uint_as_float(sv[2 * t + 1]) * kLog2eB));
+#endif
       }
+      if (ktile_masked && !kvalid) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) pk[t] = 0u;
+      }
+      if (i > 0) mbar_wait(pt_free, (i - 1) & 1);   // dV(i-1) has consumed P^T(i-1)
+      tc_fence_after();
+      tmem_st16(tmP + lane_base + 16 * c, pk);
+      if (trace) p.ts[i * 16 + 10] = clock64();
+      mbar_wait(dp_full, i & 1);
+      if (trace) p.ts[i * 16 + 11] = clock64();
+      tc_fence_after();
+      uint32_t dv[32];
+      tmem_ld32(tmdP + lane_base + c * 32, dv);
+      tmem_wait_ld();
+      uint32_t dk[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const float p0 = __uint_as_float(pk[t] << 16), p1 = __uint_as_float(pk[t] & 0xffff0000u);
+        dk[t] = pack_bf16x2(p0 * __uint_as_float(dv[2 * t]), p1 * __uint_as_float(dv[2 * t + 1]));
+      }
+      tmem_st16(tmdP + lane_base + 32 * c, dk);   // dS^T in place over this thread's own (already loaded) dP^T columns
+      if (i > 1) mbar_wait(&ds_free[i & 1], ((i - 2) >> 1) & 1);   // dQ(i-2) has consumed this smem buffer
+      const uint32_t adS = smem_u32(sdS) + (i & 1) * 2 * kTileBytes;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4)
+        st_shared_v4(adS + swz_off(r, c * 4 + q4), dk[4 * q4], dk[4 * q4 + 1], dk[4 * q4 + 2], dk[4 * q4 + 3]);
+      tmem_wait_st();
+      tc_fence_before();
+      fence_proxy_async();   // this thread's dS^T smem stores -> async proxy (dQ MMA)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
       if (trace) p.ts[i * 16 + 12] = clock64();
     }
-    // dK_j -> dqkv[:, D + h*64 ...]   (each of the two warps of a quarter stores one 32-column half)
-    if (nq > 1) mbar_wait(&pds_done[nq & 1], ((nq - 2) >> 1) & 1);          // pair nq-2 ...
-    mbar_wait(&pds_done[(nq - 1) & 1], ((nq - 1) >> 1) & 1);              // ... and the last pair have retired
+    // dK_j -> dqkv[:, D + h*64 ...]   (warps with c < 2 store one 32-column half each)
+    mbar_wait(mma_done, 0);
     tc_fence_after();
     const int kv = kt * kTile + r;
     bf16* dst = nullptr;
     if (kv < g.Lv) dst = p.dqkv_v + ((long long)b * g.Lv + kv) * (3 * g.D) + g.D + h * kHeadDim;
     else if (kv >= g.T0 && kv < g.T0 + g.Lt) dst = p.dqkv_t + ((long long)b * g.Lt + (kv - g.T0)) * (3 * g.D) + g.D + h * kHeadDim;
-    if (chunk < 2) {
+    if (c < 2) {
       uint32_t v[32];
-      tmem_ld32(tmdK + lane_base + half * 32, v);
+      tmem_ld32(tmdK + lane_base + c * 32, v);
       tmem_wait_ld();
       if (dst != nullptr) {
-        uint4* o = reinterpret_cast<uint4*>(dst + half * 32);
+        uint4* o = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
           o[q4] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * q4]), __uint_as_float(v[8 * q4 + 1])),
@@ -329,6 +427,15 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       // adjacent 16-byte chunks of the SAME row: every L2 atomic operation then covers a full 32-byte sector (half as
       // many L2 atomic operations as one-row-per-lane).  even lane keeps float4 #0,2,4,6 of its row and receives the same
       // of the odd lane's row; the odd lane keeps / receives float4 #1,3,5,7.
+#if !SIMVGB_BWD_DQ_PAIR
+      if (!(SIMVGB_DBG(p) & 1) && dst != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          red_add_v4(dst + 4 * q, __uint_as_float(v0[4 * q]), __uint_as_float(v0[4 * q + 1]), __uint_as_float(v0[4 * q + 2]), __uint_as_float(v0[4 * q + 3]));
+          red_add_v4(dst + 32 + 4 * q, __uint_as_float(v1[4 * q]), __uint_as_float(v1[4 * q + 1]), __uint_as_float(v1[4 * q + 2]), __uint_as_float(v1[4 * q + 3]));
+        }
+      }
+#else
       if (!(SIMVGB_DBG(p) & 1)) {
         const bool odd = lane & 1;
         const unsigned long long my = reinterpret_cast<unsigned long long>(dst);
@@ -361,21 +468,21 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
         flush_half(v0, 0);
         flush_half(v1, 32);
       }
+#endif
     }
-    if (nq > 1) mbar_wait(&pds_done[nq & 1], ((nq - 2) >> 1) & 1);          // pair nq-2 ...
-    mbar_wait(&pds_done[(nq - 1) & 1], ((nq - 1) >> 1) & 1);              // ... and the last pair have retired
+    mbar_wait(mma_done, 0);
     tc_fence_after();
     const int kv = kt * kTile + r;
     bf16* dst = nullptr;
     if (kv < g.Lv) dst = p.dqkv_v + ((long long)b * g.Lv + kv) * (3 * g.D) + 2 * g.D + h * kHeadDim;
     else if (kv >= g.T0 && kv < g.T0 + g.Lt) dst = p.dqkv_t + ((long long)b * g.Lt + (kv - g.T0)) * (3 * g.D) + 2 * g.D + h * kHeadDim;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int cc = 0; cc < 2; ++cc) {
       uint32_t v[32];
-      tmem_ld32(tmdV + lane_base + c * 32, v);
+      tmem_ld32(tmdV + lane_base + cc * 32, v);
       tmem_wait_ld();
       if (dst != nullptr) {
-        uint4* o = reinterpret_cast<uint4*>(dst + c * 32);
+        uint4* o = reinterpret_cast<uint4*>(dst + cc * 32);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
           o[q4] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * q4]), __uint_as_float(v[8 * q4 + 1])),
@@ -466,6 +573,8 @@ extern "C" int simvgb_attn_bwd(const simvgb_attn_args* a, void* stream) {
   if (make_attn_maps(&maps.qkv_full, &maps.qkv_tail, &maps.qkv_text, p.g, a->qkv_v, a->qkv_t, 3 * D)) return -1;
   if (make_attn_maps(&maps.do_full, &maps.do_tail, &maps.do_text, p.g, a->dout_v, a->dout_t, D)) return -1;
 
+  // positions of the virtual axis that belong to neither token range are never written by the delta kernel: keep them 0
+  SIMVGB_CUDA(cudaMemsetAsync(a->delta, 0, sizeof(float) * (size_t)a->B * a->H * lse_stride, s));
   {
     const long long n = (long long)a->B * a->Lv * a->H;
     attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const bf16*>(a->out_v),

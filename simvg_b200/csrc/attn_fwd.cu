@@ -299,7 +299,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
                              pack_bf16x2(__uint_as_float(v[8 * q4 + 6]) * inv, __uint_as_float(v[8 * q4 + 7]) * inv));
       }
     }
-    if (p.lse != nullptr && half == 0) p.lse[((long long)b * g.H + h) * (g.ntiles * kTile) + qv] = m + log2f(l);
+    // positions of the virtual axis that are not tokens get LSE = +inf: the backward then computes P = exp2(S - inf) = 0
+    // for them without any query-side masking
+    if (p.lse != nullptr && half == 0)
+      p.lse[((long long)b * g.H + h) * (g.ntiles * kTile) + qv] = dst != nullptr ? m + log2f(l) : INFINITY;
     tc_fence_before();
   }
 

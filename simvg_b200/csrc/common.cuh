@@ -8,10 +8,6 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#ifndef SIMVGB_SPIN_LIMIT
-// mbarrier waits trap instead of hanging the GPU if a pipeline is mis-wired (≈ seconds of polling).
-#define SIMVGB_SPIN_LIMIT (1u << 27)
-#endif
 
 namespace simvgb {
 
@@ -78,8 +74,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
+// re-polling.  Every poll is a shared-memory wavefront, and the shared-memory pipe is what feeds tcgen05.mma its operands:
+// without the hint an ncu capture of the attention backward showed ~1450 polling wavefronts per tile pair against ~1150
+// operand wavefronts.
+#ifndef SIMVGB_WAIT_HINT_NS
+#define SIMVGB_WAIT_HINT_NS 1000000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if SIMVGB_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SIMVGB_WAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -87,18 +99,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Blocking wait.  A mis-wired pipeline traps after ~4 s of wall time instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
 #ifdef SIMVGB_BACKOFF_NS
     __nanosleep(SIMVGB_BACKOFF_NS);   // waiting warps yield their issue slots instead of spinning
 #endif
-    if (++spins > SIMVGB_SPIN_LIMIT) {
-      printf("simvgb: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x,
-             threadIdx.x, smem_u32(bar), parity);
-      __trap();
+    if ((++spins & 63u) == 0) {
+      const uint64_t t = global_timer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) {
+        printf("simvgb: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x,
+               threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }
@@ -206,6 +231,15 @@ __device__ __forceinline__ void tmem_st16x2(uint32_t taddr, const uint32_t (&lo)
       "r"(lo[8]), "r"(lo[9]), "r"(lo[10]), "r"(lo[11]), "r"(lo[12]), "r"(lo[13]), "r"(lo[14]), "r"(lo[15]),
       "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]),
       "r"(hi[8]), "r"(hi[9]), "r"(hi[10]), "r"(hi[11]), "r"(hi[12]), "r"(hi[13]), "r"(hi[14]), "r"(hi[15])
+      : "memory");
+}
+// 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() {
