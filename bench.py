@@ -252,6 +252,16 @@ def run_ours(args, cfg_name):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Whole-step CUDA graph (simvg_b200/runtime.py): the public train-step entry point; --no-graph times the eager loop.
+    gstep = None
+    if not args.no_graph:
+        from simvg_b200.runtime import GraphedTrainStep
+        gstep = GraphedTrainStep(model, opt, ddp if world > 1 else None, warmup=max(args.warmup, 3))
+
+    def graphed_step(d, metas):
+        losses, _preds = gstep(d["img"], d["ref_expr_inds"], metas, d["text_attention_mask"], d["gt_box_t"])
+        return losses["loss_total"]
+
     def timed(n, e2e):
         """-> ms per step (device time via CUDA events, max over ranks)."""
         res, ev = upload(host[0])
@@ -264,7 +274,8 @@ def run_ours(args, cfg_name):
             cur = res
             if e2e:
                 nxt, ev = upload(host[(i + 1) % 2])      # this step's H2D copy, overlapped on the copy stream
-            loss = train_step(cur, host[i % 2]["img_metas"])
+            # graph mode: the staged device batch is copied (device->device) into the graph's static inputs, then replayed
+            loss = (graphed_step if gstep is not None else train_step)(cur, host[i % 2]["img_metas"])
             if e2e:
                 loss_host = float(loss)                  # D2H read of the step's result
                 torch.cuda.current_stream().wait_event(ev)
@@ -278,21 +289,24 @@ def run_ours(args, cfg_name):
             ms = float(t)
         return ms, loss_host
 
-    # warm-up (also warms the caching allocator)
+    # warm-up (also warms the caching allocator; in graph mode the first call captures)
     timed(max(args.warmup, 3), e2e=False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     K.reset_launch_count()
     ms, _ = timed(args.steps, e2e=False)
-    launches = K.launch_count()
+    launches = K.launch_count() if gstep is None else gstep.launches_per_step * args.steps
     ms_e2e, last_loss = timed(args.steps, e2e=True)
     clocks = sampler.stop() if rank == 0 else None
 
-    # roofline leg: one profiled step with CUDA events around every GEMM / attention launch
+    # roofline leg: one profiled EAGER step with CUDA events around every GEMM / attention launch (events cannot bracket
+    # kernels inside a graph replay); same kernels, same shapes
     res, ev = upload(host[0])
     torch.cuda.current_stream().wait_event(ev)
     torch.cuda.synchronize()
+    if gstep is not None:
+        opt.advance()
     K.profile_start()
     train_step(res, host[0]["img_metas"])
     prof = K.profile_stop()
@@ -339,7 +353,8 @@ def run_ours(args, cfg_name):
                                "full train step (fwd+loss+bwd+allreduce+clip+Adam-amsgrad)" % (cfg_name, vit, P, dec, S, S, bs),
                    "global_batch": world * bs, "seq_len": (S // P) ** 2 + 21, "parallelism": "dp%d" % world,
                    "l2": "inputs+activations per step (>40 GB) far exceed the 126 MB L2; no explicit flush",
-                   "operands": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LN / softmax / optimiser"},
+                   "operands": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LN / softmax / optimiser",
+                   "launch": "whole step replayed as one CUDA graph (simvg_b200.runtime.GraphedTrainStep)" if gstep is not None else "eager launches"},
         "clocks": clocks,
         "e2e": {"value": ips_e2e, "unit": "img/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "last_loss": last_loss},
@@ -367,6 +382,7 @@ def main():
     ap.add_argument("--dec-layers", type=int, default=0)
     ap.add_argument("--ref-batch", type=int, default=2, help="images per CPU-reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager launch loop instead of the whole-step CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, args.config)

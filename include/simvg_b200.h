@@ -157,6 +157,12 @@ int simvgb_sumsq(const float* g, int64_t n, float* out, void* stream);
 int simvgb_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, float lr, float beta1,
                         float beta2, float eps, float weight_decay, int step, const float* grad_sumsq, float max_norm,
                         void* stream);
+/* Same update with the step-dependent scalars taken from device memory: hyper = {lr, 1 - beta1^t, sqrt(1 - beta2^t)}
+ * (fp32[3]).  The launch arguments are then step-invariant, so a whole train step can be captured in a CUDA graph and the
+ * host only refreshes `hyper` before each replay. */
+int simvgb_adam_amsgrad_dev(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, const float* hyper,
+                            float beta1, float beta2, float eps, float weight_decay, const float* grad_sumsq,
+                            float max_norm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,3 +50,20 @@ def aligned_iou_giou(b1, b2):
     wh2 = (rb2 - lt2).clamp(min=0)
     area = wh2[..., 0] * wh2[..., 1]
     return iou, iou - (area - union) / area
+
+
+_SCALE_CACHE = {}
+
+
+def image_scale_tensor(img_metas, device, dtype=torch.float, repeat=2, key="img_shape"):
+    """[B, 2*repeat] tensor of (w, h[, w, h]) per image, cached per (sizes, device): building it from Python lists costs a
+    pageable host->device copy per call (a sync point, and illegal while a CUDA graph is being captured)."""
+    sizes = tuple((int(m[key][1]), int(m[key][0])) for m in img_metas)
+    k = (sizes, str(device), dtype, repeat)
+    t = _SCALE_CACHE.get(k)
+    if t is None:
+        if len(_SCALE_CACHE) > 64:
+            _SCALE_CACHE.clear()
+        t = torch.tensor([list(wh) * repeat for wh in sizes], dtype=dtype).to(device)
+        _SCALE_CACHE[k] = t
+    return t

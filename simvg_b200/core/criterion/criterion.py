@@ -120,11 +120,13 @@ class SetCriterion(nn.Module):
         """One query, one target per sample: the assignment is the identity and every loss is a batched expression."""
         from simvg_b200.core.box_ops import aligned_iou_giou
         num_boxes = float(len(targets))
-        if is_dist_avail_and_initialized():
-            nb = torch.as_tensor([num_boxes], dtype=torch.float, device=outputs["pred_logits"].device)
+        if is_dist_avail_and_initialized() and get_world_size() > 1:
+            # criterion.py:247-250 (all_reduce, / world, clamp(min=1)) kept on the device: no .item() sync, capturable
+            nb = torch.full((1,), num_boxes, dtype=torch.float, device=outputs["pred_logits"].device)
             torch.distributed.all_reduce(nb)
-            num_boxes = nb.item()
-        num_boxes = max(num_boxes / get_world_size(), 1.0)
+            num_boxes = torch.clamp(nb / get_world_size(), min=1.0)[0]
+        else:
+            num_boxes = max(num_boxes, 1.0)
         tcls = targets.labels.view(-1, 1)
         tbox = targets.boxes
 

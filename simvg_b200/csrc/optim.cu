@@ -33,7 +33,12 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
 __global__ void adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                     float* __restrict__ v, float* __restrict__ vmax, long long n, float lr, float beta1,
                                     float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-                                    const float* __restrict__ sumsq, float max_norm) {
+                                    const float* __restrict__ sumsq, float max_norm, const float* __restrict__ hyper) {
+  if (hyper != nullptr) {   // step-dependent scalars read from the device: the launch can live inside a CUDA graph
+    lr = __ldg(hyper);
+    bc1 = __ldg(hyper + 1);
+    bc2_sqrt = __ldg(hyper + 2);
+  }
   float coef = 1.0f;
   if (sumsq != nullptr && max_norm > 0.f) coef = fminf(1.0f, max_norm / (sqrtf(__ldg(sumsq)) + 1e-6f));
   const float step = lr / bc1;
@@ -102,7 +107,25 @@ extern "C" int simvgb_adam_amsgrad(float* p, const float* g, float* m, float* v,
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   adam_amsgrad_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      p, g, m, v, vmax, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_sumsq, max_norm);
+      p, g, m, v, vmax, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_sumsq, max_norm, nullptr);
+  SIMVGB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int simvgb_adam_amsgrad_dev(float* p, const float* g, float* m, float* v, float* vmax, int64_t n,
+                                       const float* hyper, float beta1, float beta2, float eps, float weight_decay,
+                                       const float* grad_sumsq, float max_norm, void* stream) {
+  SIMVGB_CHECK(p && g && m && v && vmax && hyper, "simvgb_adam_amsgrad_dev: null pointer");
+  SIMVGB_CHECK(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                 reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(vmax)) & 15) == 0,
+               "simvgb_adam_amsgrad_dev: buffers must be 16-byte aligned");
+  if (n <= 0) return 0;
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  adam_amsgrad_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, vmax, n, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, grad_sumsq, max_norm, hyper);
   SIMVGB_CUDA(cudaGetLastError());
   return 0;
 }

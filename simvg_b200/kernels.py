@@ -102,6 +102,8 @@ def _lib_setup():
         lib.simvgb_sumsq.argtypes = [L.c_vp, L.c_i64, L.c_vp, L.c_vp]
         lib.simvgb_adam_amsgrad.argtypes = [L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_i64, L.c_f32, L.c_f32, L.c_f32,
                                             L.c_f32, L.c_f32, L.c_int, L.c_vp, L.c_f32, L.c_vp]
+        lib.simvgb_adam_amsgrad_dev.argtypes = [L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_i64, L.c_vp, L.c_f32, L.c_f32,
+                                                L.c_f32, L.c_f32, L.c_vp, L.c_f32, L.c_vp]
         lib._simvgb_typed = True
     return lib
 
@@ -310,4 +312,13 @@ def adam_amsgrad(p, g, m, v, vmax, lr, beta1, beta2, eps, weight_decay, step, gr
     L.check(lib.simvgb_adam_amsgrad(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), vmax.data_ptr(), p.numel(),
                                     lr, beta1, beta2, eps, weight_decay, step, _p(grad_sumsq), max_norm, _stream()),
             "adam_amsgrad")
+    _launches[0] += 1
+
+
+def adam_amsgrad_dev(p, g, m, v, vmax, hyper, beta1, beta2, eps, weight_decay, grad_sumsq=None, max_norm=0.0):
+    """Adam(amsgrad) with {lr, 1-beta1^t, sqrt(1-beta2^t)} read from the device tensor `hyper` (graph-capturable)."""
+    lib = _lib_setup()
+    L.check(lib.simvgb_adam_amsgrad_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), vmax.data_ptr(), p.numel(),
+                                        hyper.data_ptr(), beta1, beta2, eps, weight_decay, _p(grad_sumsq), max_norm,
+                                        _stream()), "adam_amsgrad_dev")
     _launches[0] += 1

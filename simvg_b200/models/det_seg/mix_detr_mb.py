@@ -8,7 +8,7 @@ reference's transpose+reshape at :52/:108, no copy), and the REC prediction path
 import torch
 import torch.nn.functional as F
 
-from simvg_b200.core.box_ops import box_cxcywh_to_xyxy
+from simvg_b200.core.box_ops import box_cxcywh_to_xyxy, image_scale_tensor
 from simvg_b200.models.builder import MODELS
 from simvg_b200.structures import detector_postprocess
 
@@ -63,9 +63,7 @@ class MIXDETRMB(OneStageModel):
             return dict(pred_bboxes=None, pred_masks=None, predict_classes=None)
         B, nq = box_cls.shape[:2]
         scores, labels = F.softmax(box_cls, dim=-1)[:, :, :-1].max(-1)
-        hw = torch.tensor([[m["img_shape"][1], m["img_shape"][0]] for m in img_metas], dtype=box_pred.dtype)
-        hw = hw.to(box_pred.device, non_blocking=True)                                     # [B, (w, h)]
-        whwh = torch.cat([hw, hw], dim=1).unsqueeze(1)
+        whwh = image_scale_tensor(img_metas, box_pred.device, box_pred.dtype, repeat=2).unsqueeze(1)   # [B, 1, (w, h, w, h)]
         boxes = box_cxcywh_to_xyxy(box_pred) * whwh
         boxes = torch.min(boxes.clamp(min=0), whwh)
         keep = ((boxes[..., 2] - boxes[..., 0]) > 0) & ((boxes[..., 3] - boxes[..., 1]) > 0)

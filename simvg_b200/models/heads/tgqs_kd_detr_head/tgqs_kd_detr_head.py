@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from simvg_b200 import ops
-from simvg_b200.core.box_ops import aligned_iou_giou, box_cxcywh_to_xyxy, box_iou, box_xyxy_to_cxcywh
+from simvg_b200.core.box_ops import aligned_iou_giou, box_cxcywh_to_xyxy, box_iou, box_xyxy_to_cxcywh, image_scale_tensor
 from simvg_b200.core.criterion.criterion import BatchedTargets, HungarianMatcher, SetCriterion
 from simvg_b200.models.builder import HEADS
 from simvg_b200.models.heads.utils import MLP, PositionEmbeddingSine1D
@@ -118,8 +118,7 @@ class TextGuidedQuerySelectKDDETRHead(nn.Module):
         scores = F.softmax(logits, dim=-1)[:, :, 0:1]
         dev = logits.device
         if self._is_rec(targets):
-            whwh = torch.tensor([[m["img_shape"][1], m["img_shape"][0], m["img_shape"][1], m["img_shape"][0]] for m in img_metas],
-                                dtype=torch.float).to(dev, non_blocking=True)
+            whwh = image_scale_tensor(img_metas, dev, torch.float, repeat=2)
             gt = box_xyxy_to_cxcywh(torch.stack([t.to(dev) for t in targets]).float() / whwh).float()  # [B, 4]
             zeros = torch.zeros(len(targets), 1, dtype=torch.int64, device=dev)
             new_gt = BatchedTargets([{"labels": zeros[i], "boxes": gt[i:i + 1]} for i in range(len(targets))],

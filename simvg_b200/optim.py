@@ -52,6 +52,29 @@ class FusedAdamAMSGrad:
             s.fb.ensure()
             s.fb.attach_grads()
         self._sumsq = None
+        self._hyper = None        # device [n_segments, 4]: lr, 1 - beta1^t, sqrt(1 - beta2^t), pad  (graph mode)
+        self._hyper_host = None   # pinned mirror
+        self.graph_mode = False
+
+    # ---- CUDA-graph support: step-dependent scalars live in device memory, refreshed by advance() before each replay
+    def enable_graph_mode(self):
+        dev = self.segments[0].fb.data.device
+        self._hyper = torch.zeros(len(self.segments), 4, device=dev, dtype=torch.float32)
+        self._hyper_host = torch.zeros(len(self.segments), 4, dtype=torch.float32).pin_memory()
+        self.graph_mode = True
+        for s in self.segments:
+            s.ensure_state()
+        if self._sumsq is None or self._sumsq.device != dev:
+            self._sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+
+    def advance(self):
+        """Graph mode: t += 1 and upload this step's {lr, bias corrections} (async, on the current stream)."""
+        self.t += 1
+        for i, s in enumerate(self.segments):
+            self._hyper_host[i, 0] = s.lr
+            self._hyper_host[i, 1] = 1.0 - self.betas[0] ** self.t
+            self._hyper_host[i, 2] = (1.0 - self.betas[1] ** self.t) ** 0.5
+        self._hyper.copy_(self._hyper_host, non_blocking=True)
 
     @property
     def param_groups(self):  # scheduler-facing view (core/scheduler.py multiplies group["lr"])
@@ -65,6 +88,8 @@ class FusedAdamAMSGrad:
             s.fb.zero_grad()
 
     def step(self):
+        if self.graph_mode:
+            return self._step_graph()
         self.t += 1
         dev = self.segments[0].fb.data.device
         if self._sumsq is None or self._sumsq.device != dev:
@@ -78,6 +103,17 @@ class FusedAdamAMSGrad:
             s.ensure_state()
             K.adam_amsgrad(s.fb.data, s.fb.grad, s.m, s.v, s.vmax, s.lr, self.betas[0], self.betas[1], self.eps,
                            self.weight_decay, self.t, grad_sumsq=self._sumsq if clip > 0 else None, max_norm=clip)
+
+    def _step_graph(self):
+        """Same update with step-invariant launch arguments (advance() must have been called for this step)."""
+        clip = float(self.grad_norm_clip) if self.grad_norm_clip else 0.0
+        if clip > 0:
+            self._sumsq.zero_()
+            for s in self.segments:
+                K.sumsq(s.fb.grad, self._sumsq)
+        for i, s in enumerate(self.segments):
+            K.adam_amsgrad_dev(s.fb.data, s.fb.grad, s.m, s.v, s.vmax, self._hyper[i], self.betas[0], self.betas[1], self.eps,
+                               self.weight_decay, grad_sumsq=self._sumsq if clip > 0 else None, max_norm=clip)
 
     def grad_norm(self):
         """Global gradient norm of the last step() (device scalar; reading it synchronises)."""

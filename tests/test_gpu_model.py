@@ -129,3 +129,51 @@ def test_training_reduces_loss_and_droppath_runs(lib):
     assert all(h == h for h in hist) and min(hist[-3:]) < hist[0], hist
     sd = opt.state_dict()
     assert len(sd["param_groups"]) == 2 and sd["param_groups"][0]["lr"] == 2e-5
+
+
+def test_graphed_train_step_matches_eager(lib):
+    """GraphedTrainStep (whole step captured in one CUDA graph, Adam scalars read from the device) reproduces the eager
+    train loop: same losses step by step and the same parameters afterwards (stochastic layers off so runs are comparable)."""
+    from simvg_b200.models import build_model
+    from simvg_b200.optim import FusedAdamAMSGrad
+    from simvg_b200.runtime import GraphedTrainStep
+    from tools.synth import make_batch, model_cfg
+
+    def make():
+        torch.manual_seed(5)
+        m = build_model(model_cfg("base", 128, 32, drop_path_rate=0.0)).cuda().train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+            if isinstance(mod, torch.nn.MultiheadAttention):
+                mod.dropout = 0.0
+            if hasattr(mod, "attn_drop") and isinstance(mod.attn_drop, float):
+                mod.attn_drop = 0.0
+        return m, FusedAdamAMSGrad(m, lr=2e-4, lr_vis_enc=2e-5, grad_norm_clip=0.15)
+
+    batches = [make_batch(4, 128, seed=10 + i, device="cuda") for i in range(2)]
+    m1, o1 = make()
+    eager = []
+    for it in range(5):
+        b = batches[it % 2]
+        o1.zero_grad()
+        losses, _ = m1(b["img"], b["ref_expr_inds"], b["img_metas"], return_loss=True,
+                       text_attention_mask=b["text_attention_mask"], gt_bbox=b["gt_bbox"])
+        losses["loss_total"].backward()
+        o1.step()
+        eager.append(float(losses["loss_total"]))
+    m2, o2 = make()
+    step = GraphedTrainStep(m2, o2, warmup=0)
+    graphed = []
+    for it in range(5):
+        b = batches[it % 2]
+        losses, preds = step(b["img"], b["ref_expr_inds"], b["img_metas"], b["text_attention_mask"], torch.stack(b["gt_bbox"]))
+        graphed.append(float(losses["loss_total"]))
+    assert step.launches_per_step > 100
+    assert o2.t == o1.t == 5
+    for a, g in zip(eager, graphed):
+        assert abs(a - g) <= 2e-3 * abs(a), (eager, graphed)
+    p1 = torch.cat([p.detach().flatten() for p in m1.parameters()])
+    p2 = torch.cat([p.detach().flatten() for p in m2.parameters()])
+    assert rel(p2, p1) < 1e-3
+    assert preds[0]["pred_bboxes"].shape == (4, 4)
