@@ -380,6 +380,63 @@ __device__ __forceinline__ float gelu_fwd_grad(float x, float& g) {
   return fmaf(x, pdf, cdf);
 }
 
+// ---- packed fp32x2 math (FFMA2 / FMUL2 / FADD2: one issue slot per TWO lanes-worth of fp32 work).  The row kernels that
+// apply GELU are bound by instruction issue, not by HBM; the packed forms roughly halve their FMA-pipe instruction count.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// Phi(x) = 0.5 (1 + erf(x / sqrt 2)) for two values: the A&S 7.1.28 polynomial of erf_fast with 2^(-k/2) folded into the
+// coefficients, evaluated with packed FMAs.
+__device__ __forceinline__ float2 gelu_cdf2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  float2 p = fma2(splat2(0.0000430638f * 0.125f), ax, splat2(0.0002765672f * 0.17677669529663688f));
+  p = fma2(p, ax, splat2(0.0001520143f * 0.25f));
+  p = fma2(p, ax, splat2(0.0092705272f * 0.35355339059327376f));
+  p = fma2(p, ax, splat2(0.0422820123f * 0.5f));
+  p = fma2(p, ax, splat2(0.0705230784f * 0.70710678118654752f));
+  p = fma2(p, ax, splat2(1.0f));
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(p.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(p.y));
+  r = mul2(r, r); r = mul2(r, r); r = mul2(r, r); r = mul2(r, r);   // p^-16 = 1 - erf(|x| / sqrt 2)
+  float2 h = fma2(r, splat2(-0.5f), splat2(0.5f));                  // 0.5 erf(|x| / sqrt 2)
+  h.x = copysignf(h.x, x.x);
+  h.y = copysignf(h.y, x.y);
+  return add2(h, splat2(0.5f));
+}
+__device__ __forceinline__ float2 gelu_fwd2(float2 x) { return mul2(x, gelu_cdf2(x)); }
+// g = gelu(x), returns d gelu / dx
+__device__ __forceinline__ float2 gelu_fwd_grad2(float2 x, float2& g) {
+  const float2 cdf = gelu_cdf2(x);
+  const float2 t = mul2(mul2(x, x), splat2(-0.72134752044448170368f));
+  const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+  g = mul2(x, cdf);
+  return fma2(x, mul2(e, splat2(0.3989422804014327f)), cdf);
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }

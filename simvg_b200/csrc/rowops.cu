@@ -130,23 +130,27 @@ __global__ void __launch_bounds__(128) ln_fwd_warp_kernel(const TIn* __restrict_
     float v[NCH][8];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) load8(x + row * C + (c * 32 + lane) * 8, v[c]);
-    float s = 0.f;
+    float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (GELU) v[c][i] = gelu_fwd(v[c][i]);
-        s += v[c][i];
+      for (int i = 0; i < 8; i += 2) {
+        float2 t = make_float2(v[c][i], v[c][i + 1]);
+        if (GELU) t = gelu_fwd2(t);
+        v[c][i] = t.x; v[c][i + 1] = t.y;
+        s2 = add2(s2, t);
       }
     }
-    const float mu = warp_sum(s) * (1.0f / C);
-    float q = 0.f;
+    const float mu = warp_sum(s2.x + s2.y) * (1.0f / C);
+    float2 q2 = make_float2(0.f, 0.f);
+    const float2 nmu = splat2(-mu);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = v[c][i] - mu; q += d * d; }
+      for (int i = 0; i < 8; i += 2) { const float2 d = add2(make_float2(v[c][i], v[c][i + 1]), nmu); q2 = fma2(d, d, q2); }
     }
-    const float rs = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+    const float rs = rsqrtf(warp_sum(q2.x + q2.y) * (1.0f / C) + eps);
+    const float2 rs2 = splat2(rs), nmurs = splat2(-mu * rs);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = (c * 32 + lane) * 8;
@@ -154,7 +158,11 @@ __global__ void __launch_bounds__(128) ln_fwd_warp_kernel(const TIn* __restrict_
       load8(gamma + col, g);
       load8(beta + col, bt);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (v[c][i] - mu) * rs * g[i] + bt[i];
+      for (int i = 0; i < 8; i += 2) {
+        const float2 xh = fma2(make_float2(v[c][i], v[c][i + 1]), rs2, nmurs);
+        const float2 r = fma2(xh, make_float2(g[i], g[i + 1]), make_float2(bt[i], bt[i + 1]));
+        o[i] = r.x; o[i + 1] = r.y;
+      }
       store8(y + row * C + col, o);
     }
     if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
@@ -472,35 +480,50 @@ __global__ void __launch_bounds__(128) ln_bwd_wide_kernel(const LnBwdParams p) {
     prefetch(row + gridDim.x);
     float xh[NCH][8], dyg[NCH][8], gg[NCH][8];
     float s1 = 0.f, s2 = 0.f;
+    float2 s1v = make_float2(0.f, 0.f), s2v = make_float2(0.f, 0.f);
+    const float2 rs2 = splat2(rs), nmurs = splat2(-mu * rs);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       unpack8(cu[c], cu[c], false, xh[c]);
       unpack8(cdy[c], cdy[c], false, dyg[c]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float gv;
-        gg[c][i] = gelu_fwd_grad(xh[c][i], gv);
-        xh[c][i] = (gv - mu) * rs;
-        acc_g[c][i] += dyg[c][i] * xh[c][i];
-        acc_b[c][i] += dyg[c][i];
-        dyg[c][i] *= g[c][i];
-        s1 += dyg[c][i];
-        s2 += dyg[c][i] * xh[c][i];
+      for (int i = 0; i < 8; i += 2) {
+        float2 gv;
+        const float2 gd = gelu_fwd_grad2(make_float2(xh[c][i], xh[c][i + 1]), gv);
+        gg[c][i] = gd.x; gg[c][i + 1] = gd.y;
+        const float2 xn = fma2(gv, rs2, nmurs);
+        xh[c][i] = xn.x; xh[c][i + 1] = xn.y;
+        float2 dy2 = make_float2(dyg[c][i], dyg[c][i + 1]);
+        const float2 ag = fma2(dy2, xn, make_float2(acc_g[c][i], acc_g[c][i + 1]));
+        acc_g[c][i] = ag.x; acc_g[c][i + 1] = ag.y;
+        const float2 ab = add2(dy2, make_float2(acc_b[c][i], acc_b[c][i + 1]));
+        acc_b[c][i] = ab.x; acc_b[c][i + 1] = ab.y;
+        dy2 = mul2(dy2, make_float2(g[c][i], g[c][i + 1]));
+        dyg[c][i] = dy2.x; dyg[c][i + 1] = dy2.y;
+        s1v = add2(s1v, dy2);
+        s2v = fma2(dy2, xn, s2v);
       }
     }
+    s1 = s1v.x + s1v.y;
+    s2 = s2v.x + s2v.y;
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
     if (lane == 0) { red[par][warp][0] = s1; red[par][warp][1] = s2; }
     __syncthreads();
     const float c1 = (red[par][0][0] + red[par][1][0] + red[par][2][0] + red[par][3][0]) * (1.0f / C);
     const float c2 = (red[par][0][1] + red[par][1][1] + red[par][2][1] + red[par][3][1]) * (1.0f / C);
+    const float2 nc1 = splat2(-c1), nc2 = splat2(-c2);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       float dx[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        dx[i] = rs * (dyg[c][i] - c1 - xh[c][i] * c2) * gg[c][i];
-        acc_p[c][i] += dx[i];
+      for (int i = 0; i < 8; i += 2) {
+        // rs * (dy*gamma - c1 - xhat * c2) * gelu'(u)
+        const float2 t = fma2(make_float2(xh[c][i], xh[c][i + 1]), nc2, add2(make_float2(dyg[c][i], dyg[c][i + 1]), nc1));
+        const float2 d = mul2(mul2(t, rs2), make_float2(gg[c][i], gg[c][i + 1]));
+        dx[i] = d.x; dx[i + 1] = d.y;
+        const float2 ap = add2(d, make_float2(acc_p[c][i], acc_p[c][i + 1]));
+        acc_p[c][i] = ap.x; acc_p[c][i + 1] = ap.y;
       }
       store8(p.dx + row * C + col0 + c * 256, dx);
     }

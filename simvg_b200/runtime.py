@@ -52,11 +52,21 @@ class GraphedTrainStep:
             for _ in range(self.warmup):   # real optimiser steps: allocator / workspace / NCCL warm-up before capture
                 self.opt.advance()
                 self._eager(self.static, metas)
+            if self.warmup == 0:
+                # one forward + backward without an optimiser step: fills the model's host-built caches (position
+                # encodings, image-size tensors, attention workspaces, kernel attributes) without touching the parameters
+                self.opt.zero_grad()
+                losses, _ = self.model(self.static["img"], self.static["ids"], metas, return_loss=True,
+                                       text_attention_mask=self.static["mask"], gt_bbox=list(self.static["gt"].unbind(0)))
+                losses["loss_total"].backward()
+                if self.ddp is not None:
+                    self.ddp.finish()
+                del losses
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         K.reset_launch_count()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):   # same stream as the warm-up: autograd's AccumulateGrad nodes stay on it
             losses, preds = self._eager(self.static, metas)
         self.launches_per_step = K.launch_count()
         self.out = (losses, preds)
