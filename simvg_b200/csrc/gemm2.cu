@@ -20,6 +20,9 @@
 
 namespace simvgb {
 
+#ifndef SIMVGB_GEMM_STAGED_EPI
+#define SIMVGB_GEMM_STAGED_EPI 1
+#endif
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kEpiWarps = 8;
@@ -31,7 +34,9 @@ struct Gemm2Cfg {
   static constexpr int kBBytes = 128 * BK * 2;       // 16 KB: this CTA's half (128 rows) of the 256-wide B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 512;              // 2 x 256 fp32 columns (double-buffered accumulators)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kEpiStageBytes = 32 * 32 * 4; // per epilogue warp: one 32 x 32 fp32 chunk, transposed through smem so that
+                                                     // global accesses cover whole 64/128-byte row segments
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 + 256;
 };
 
 struct GemmParams {
@@ -65,7 +70,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                              ~uintptr_t(1023));
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smemEpi = smem + Cfg::kStages * Cfg::kStageBytes;   // [kEpiWarps][4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemEpi + kEpiWarps * Cfg::kEpiStageBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + Cfg::kStages;       // [kStages]
   uint64_t* acc_full = bars + 2 * Cfg::kStages;   // [2]
@@ -204,6 +210,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t v[32];
         tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + c * 32, v);
         tmem_wait_ld();
+        const bool chunk_rows_ok = (m0 + quarter * 32 + 32) <= p.M;   // warp-uniform: all 32 rows of this warp exist
         if (col0 >= p.N || !row_ok) continue;
         float f[32];
 #pragma unroll
@@ -223,6 +230,64 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
         const long long off = (long long)row * p.ldo + col0;
+#if SIMVGB_GEMM_STAGED_EPI
+        // ---- coalesced path (full 32-column chunks): with one output row per lane every 16-byte access of a warp lands in
+        // a different 128-byte line (32 line requests per instruction — the residual epilogue of the K=768 GEMMs was LSU-
+        // bound at 2.7x the tile's MMA time).  The chunk is transposed through a private 4 KB smem slab (XOR-swizzled,
+        // conflict-free both ways) so that 8 (fp32) / 4 (bf16) lanes cover one contiguous row segment.
+        if (full_chunk && chunk_rows_ok && (p.epilogue == SIMVGB_EPI_RESID || p.epilogue == SIMVGB_EPI_BF16 ||
+                                            (p.epilogue == SIMVGB_EPI_F32 && !p.accumulate))) {
+          const uint32_t slab = smem_u32(smemEpi + ew * Cfg::kEpiStageBytes);
+          const long long row0 = m0 + quarter * 32;
+          if (p.epilogue == SIMVGB_EPI_BF16) {
+            if (col0 + 32 <= p.scale_cols) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= p.scale;
+            } else if (col0 < p.scale_cols) {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.scale_cols) f[j] *= p.scale;
+            }
+            // rows of 64 B; 16-byte slot s of row r lives at r*64 + ((s ^ ((r >> 1) & 3)) << 4)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              st_shared_v4(slab + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pack_bf16x2(f[8 * j], f[8 * j + 1]),
+                           pack_bf16x2(f[8 * j + 2], f[8 * j + 3]), pack_bf16x2(f[8 * j + 4], f[8 * j + 5]),
+                           pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = 8 * i + (lane >> 2), sl = lane & 3;
+              const uint4 v4 = ld_shared_v4(slab + r * 64 + ((sl ^ ((r >> 1) & 3)) << 4));
+              *reinterpret_cast<uint4*>(p.out_bf16 + (row0 + r) * p.ldo + col0 + 8 * sl) = v4;
+            }
+          } else {
+            if (p.epilogue == SIMVGB_EPI_RESID) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= rs;
+            }
+            // rows of 128 B; 16-byte slot s of row r lives at r*128 + ((s ^ (r & 7)) << 4)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(slab + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                           __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + (lane >> 3), sl = lane & 7;
+              const uint4 v4 = ld_shared_v4(slab + r * 128 + ((sl ^ (r & 7)) << 4));
+              float4 o4 = make_float4(__uint_as_float(v4.x), __uint_as_float(v4.y), __uint_as_float(v4.z), __uint_as_float(v4.w));
+              const long long o = (row0 + r) * p.ldo + col0 + 4 * sl;
+              if (p.epilogue == SIMVGB_EPI_RESID) {
+                const float4 rv = __ldg(reinterpret_cast<const float4*>(p.res_f32 + o));
+                o4.x += rv.x; o4.y += rv.y; o4.z += rv.z; o4.w += rv.w;
+              }
+              *reinterpret_cast<float4*>(p.out_f32 + o) = o4;
+            }
+          }
+          __syncwarp();   // the slab is reused by the next chunk
+          continue;
+        }
+#endif
         switch (p.epilogue) {
           case SIMVGB_EPI_BF16: {
             if (col0 + 32 <= p.scale_cols) {
