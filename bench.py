@@ -254,7 +254,9 @@ def run_ours(args, cfg_name):
 
     # Whole-step CUDA graph (simvg_b200/runtime.py): the public train-step entry point; --no-graph times the eager loop.
     gstep = None
-    if not args.no_graph:
+    # world > 1: eager launches.  Capturing the NCCL gradient all-reduces inside the step graph hung at N=2 in round 1
+    # (gpurun_out/s2_bench_n2.err) and is left for the next round; the data-parallel path itself is unchanged.
+    if not args.no_graph and world == 1:
         from simvg_b200.runtime import GraphedTrainStep
         gstep = GraphedTrainStep(model, opt, ddp if world > 1 else None, warmup=max(args.warmup, 3))
 

@@ -65,3 +65,35 @@ def test_flat_ddp_world2_gloo(tmp_path):
     want = (r0["local"] + r1["local"]) / 2
     assert torch.allclose(r0["avg"], want, atol=1e-7) and torch.equal(r0["avg"], r1["avg"])
     assert float(want.abs().sum()) > 0
+
+
+def _crit_worker(rank, world, port, out):
+    """REC criterion under torch.distributed: num_boxes = clamp(all_reduce(B) / world, 1) stays a device tensor (no .item())."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from simvg_b200.core.criterion.criterion import BatchedTargets, HungarianMatcher, SetCriterion
+    g = torch.Generator().manual_seed(7 + rank)
+    B = 3 + rank                                    # different local batch sizes: the all-reduce matters
+    logits, boxes = torch.randn(B, 1, 2, generator=g), torch.rand(B, 1, 4, generator=g) * 0.4 + 0.2
+    gt = torch.rand(B, 4, generator=g) * 0.3 + 0.3
+    zeros = torch.zeros(B, 1, dtype=torch.int64)
+    plain = [{"labels": zeros[i], "boxes": gt[i:i + 1]} for i in range(B)]
+    batched = BatchedTargets(plain, boxes=gt, labels=zeros[:, 0])
+    crit = SetCriterion(1, HungarianMatcher(1, 5.0, 2.0, "ce_cost"), {"loss_class": 1, "loss_bbox": 5.0, "loss_giou": 2.0},
+                        loss_class_type="ce_loss", eos_coef=0.1)
+    outp = {"pred_logits": logits, "pred_boxes": boxes}
+    fast, generic = crit(outp, batched), crit(outp, plain)
+    torch.save({"fast": {k: float(v) for k, v in fast.items()}, "generic": {k: float(v) for k, v in generic.items()},
+                "l1_sum": float(torch.nn.functional.l1_loss(boxes[:, 0], gt, reduction="none").sum()), "B": B},
+               os.path.join(out, "c%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_rec_criterion_num_boxes_world2_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_crit_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        d = torch.load(tmp_path / ("c%d.pt" % r))
+        for k, v in d["generic"].items():           # generic path = the reference's arithmetic (all_reduce + .item())
+            assert abs(d["fast"][k] - v) <= 1e-6 * max(abs(v), 1.0), (r, k, d["fast"][k], v)
+        assert abs(d["fast"]["loss_bbox"] - d["l1_sum"] / 3.5) < 1e-5   # (3 + 4) boxes / 2 ranks
