@@ -68,6 +68,10 @@ typedef struct simvgb_gemm_args {
 } simvgb_gemm_args;
 
 int simvgb_gemm(const simvgb_gemm_args* args, void* stream);
+/* Two independent problems in ONE persistent launch: SimVG's multiway layers run every projection twice (vision-token
+ * expert, text-token expert: torchscale MultiwayNetwork); the text problem is ~80x smaller and, launched on
+ * its own, is pure launch/ramp latency.  Equivalent to simvgb_gemm(a) followed by simvgb_gemm(b). */
+int simvgb_gemm_pair(const simvgb_gemm_args* a, const simvgb_gemm_args* b, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused multiway self-attention (flash-style; S, O, dK, dV, dQ accumulators in TMEM).

@@ -379,10 +379,10 @@ static int launch_gemm(const simvgb_gemm_args* a, cudaStream_t stream) {
 }  // namespace simvgb
 
 namespace simvgb {
-int launch_gemm_2cta(const simvgb_gemm_args* a, cudaStream_t stream);
+int launch_gemm_2cta(const simvgb_gemm_args* a, const simvgb_gemm_args* b, cudaStream_t stream);
 }
 
-extern "C" int simvgb_gemm(const simvgb_gemm_args* a, void* stream) {
+static int simvgb_gemm_validate(const simvgb_gemm_args* a) {
   using namespace simvgb;
   SIMVGB_CHECK(a != nullptr, "simvgb_gemm: null args");
   SIMVGB_CHECK(a->M > 0 && a->N > 0 && a->K > 0, "simvgb_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
@@ -399,11 +399,34 @@ extern "C" int simvgb_gemm(const simvgb_gemm_args* a, void* stream) {
     case SIMVGB_EPI_RESID: SIMVGB_CHECK(a->out_f32 && a->res_f32, "simvgb_gemm: RESID needs out_f32 and res_f32"); break;
     default: SIMVGB_CHECK(a->out_f32, "simvgb_gemm: out_f32 is null"); break;
   }
+  return 0;
+}
+
+static bool simvgb_use_2cta(const simvgb_gemm_args* a) {
+  static const int use_2cta = [] { const char* e = getenv("SIMVGB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+  return use_2cta && a->N > 128 && a->M >= 256;
+}
+
+extern "C" int simvgb_gemm(const simvgb_gemm_args* a, void* stream) {
+  using namespace simvgb;
+  if (int rc = simvgb_gemm_validate(a)) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // Large problems: 2-CTA (cta_group::2) 256x256 tiles.  SIMVGB_GEMM_2CTA=0 forces the 1-CTA kernel (A/B testing).
-  static const int use_2cta = [] { const char* e = getenv("SIMVGB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
-  if (use_2cta && a->N > 128 && a->M >= 256) return launch_gemm_2cta(a, s);
+  if (simvgb_use_2cta(a)) return launch_gemm_2cta(a, nullptr, s);
   // BN=256 tiles unless N is small (head projections, N<=128) where half the tile would be masked.
   if (a->N > 128) return launch_gemm<256>(a, s);
   return launch_gemm<128>(a, s);
+}
+
+// Two independent GEMMs in one persistent launch (the vision-expert and text-expert problems of one multiway layer).
+// Falls back to two launches when either problem is not eligible for the 2-CTA kernel.
+extern "C" int simvgb_gemm_pair(const simvgb_gemm_args* a, const simvgb_gemm_args* b, void* stream) {
+  using namespace simvgb;
+  if (int rc = simvgb_gemm_validate(a)) return rc;
+  if (int rc = simvgb_gemm_validate(b)) return rc;
+  static const int pair_ok = [] { const char* e = getenv("SIMVGB_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  if (pair_ok && simvgb_use_2cta(a) && simvgb_use_2cta(b))
+    return launch_gemm_2cta(a, b, reinterpret_cast<cudaStream_t>(stream));
+  if (int rc = simvgb_gemm(a, stream)) return rc;
+  return simvgb_gemm(b, stream);
 }

@@ -60,8 +60,11 @@ struct GemmParams {
 __device__ __forceinline__ float gelu_erf(float x) { return gelu_fwd(x); }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const GemmParams p) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+             const __grid_constant__ GemmParams p0, const __grid_constant__ CUtensorMap tmA1,
+             const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ GemmParams p1, const int tiles1) {
+  // Two independent problems may share one persistent launch (SimVG's multiway experts: the vision-token GEMM and the
+  // 80x smaller text-token GEMM of the same layer).  Tiles of problem 0 come first; the tiles of problem 1 fill the tail.
   using Cfg = Gemm2Cfg;
   constexpr int BN = 256;
   const uint32_t cta = cluster_ctarank();   // 0 = leader (issues the MMAs), 1 = peer
@@ -82,8 +85,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (tiles1 > 0) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -106,7 +113,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // shfl from a fixed lane => provably warp-uniform
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;   // m_tiles counts 256-row tiles
+  const int tiles0 = p0.m_tiles * p0.n_tiles * p0.k_splits;   // m_tiles counts 256-row tiles
+  const int total_tiles = tiles0 + tiles1;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0) {
@@ -114,7 +122,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      for (int tt = cluster_id; tt < total_tiles; tt += num_clusters) {
+        const bool second = tt >= tiles0;
+        const GemmParams& p = second ? p1 : p0;
+        const CUtensorMap& tmA = second ? tmA1 : tmA0;
+        const CUtensorMap& tmB = second ? tmB1 : tmB0;
+        const int t = second ? tt - tiles0 : tt;
         const int split = t % p.k_splits;
         const int mn = t / p.k_splits;
         const int m0 = (mn / p.n_tiles) * 256 + cta * BM;       // this CTA's 128 rows of the 256-row tile
@@ -150,16 +163,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ===================== MMA issuer =====================
     // The whole warp runs this loop with warp-uniform values (descriptors stay in uniform registers); only the
     // tcgen05.mma / tcgen05.commit instructions themselves are issued by one lane.
-    const uint32_t idesc = umma_idesc_bf16(256, BN, p.a_mn, p.b_mn);   // M = 256 across the CTA pair
-    // K-major: 8-row groups 1024 B apart; UMMA_K=16 -> +32 B.  MN-major: next 64-wide atom 8192 B
-    // away (LBO), 8 k-row groups 1024 B apart (SBO); UMMA_K=16 -> +16 rows = 2048 B.
-    const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
-    const uint32_t a_kstep = p.a_mn ? (2048u >> 4) : (32u >> 4), b_kstep = p.b_mn ? (2048u >> 4) : (32u >> 4);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+    for (int tt = cluster_id; tt < total_tiles; tt += num_clusters) {
+      const bool second = tt >= tiles0;
+      const GemmParams& p = second ? p1 : p0;
+      const int t = second ? tt - tiles0 : tt;
+      const uint32_t idesc = umma_idesc_bf16(256, BN, p.a_mn, p.b_mn);   // M = 256 across the CTA pair
+      // K-major: 8-row groups 1024 B apart; UMMA_K=16 -> +32 B.  MN-major: next 64-wide atom 8192 B
+      // away (LBO), 8 k-row groups 1024 B apart (SBO); UMMA_K=16 -> +16 rows = 2048 B.
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+      const uint32_t a_kstep = p.a_mn ? (2048u >> 4) : (32u >> 4), b_kstep = p.b_mn ? (2048u >> 4) : (32u >> 4);
       const int split = t % p.k_splits;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -192,7 +208,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     constexpr int kChunksPerHalf = BN / 64;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+    for (int tt = cluster_id; tt < total_tiles; tt += num_clusters) {
+      const bool second = tt >= tiles0;
+      const GemmParams& p = second ? p1 : p0;
+      const int t = second ? tt - tiles0 : tt;
       const int mn = t / p.k_splits;
       const int m0 = (mn / p.n_tiles) * 256 + cta * BM;
       const int n0 = (mn % p.n_tiles) * BN;
@@ -393,23 +412,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 
-// Host launch.  Returns 1 if the shape is not eligible (caller falls back to the 1-CTA kernel).
-int launch_gemm_2cta(const simvgb_gemm_args* a, cudaStream_t stream) {
+// Host side.
+static int prepare_2cta(const simvgb_gemm_args* a, CUtensorMap* tmA, CUtensorMap* tmB, GemmParams* pp) {
   constexpr int BN = 256;
-  CUtensorMap tmA, tmB;
   {
     uint64_t dims[2], strides[1];
     uint32_t box[2];
     if (!a->a_mn_major) { dims[0] = a->K; dims[1] = a->M; box[0] = BK; box[1] = BM; }
     else                { dims[0] = a->M; dims[1] = a->K; box[0] = 64; box[1] = BK; }
     strides[0] = (uint64_t)a->lda * 2;
-    if (make_tmap(&tmA, a->A, 2, 2, dims, strides, box, 1)) return -1;
+    if (make_tmap(tmA, a->A, 2, 2, dims, strides, box, 1)) return -1;
     if (!a->b_mn_major) { dims[0] = a->K; dims[1] = a->N; box[0] = BK; box[1] = BN / 2; }
     else                { dims[0] = a->N; dims[1] = a->K; box[0] = 64; box[1] = BK; }
     strides[0] = (uint64_t)a->ldb * 2;
-    if (make_tmap(&tmB, a->B, 2, 2, dims, strides, box, 1)) return -1;
+    if (make_tmap(tmB, a->B, 2, 2, dims, strides, box, 1)) return -1;
   }
-  GemmParams p;
+  GemmParams& p = *pp;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.a_mn = a->a_mn_major; p.b_mn = a->b_mn_major;
   p.m_tiles = (a->M + 255) / 256;
@@ -431,15 +449,30 @@ int launch_gemm_2cta(const simvgb_gemm_args* a, cudaStream_t stream) {
   p.row_scale = a->row_scale;
   p.rows_per_scale = a->rows_per_scale > 0 ? a->rows_per_scale : 1;
   p.accumulate = a->accumulate;
+  return 0;
+}
+
+// Launches problem `a` and, when b != nullptr, problem `b` in the same persistent grid.
+int launch_gemm_2cta(const simvgb_gemm_args* a, const simvgb_gemm_args* b, cudaStream_t stream) {
+  CUtensorMap tmA0, tmB0, tmA1, tmB1;
+  GemmParams p0, p1;
+  if (prepare_2cta(a, &tmA0, &tmB0, &p0)) return -1;
+  int tiles1 = 0;
+  if (b != nullptr) {
+    if (prepare_2cta(b, &tmA1, &tmB1, &p1)) return -1;
+    tiles1 = p1.m_tiles * p1.n_tiles * p1.k_splits;
+  } else {
+    tmA1 = tmA0; tmB1 = tmB0; p1 = p0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     SIMVGB_CUDA(cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int total = p.m_tiles * p.n_tiles * p.k_splits;
+  const int total = p0.m_tiles * p0.n_tiles * p0.k_splits + tiles1;
   int clusters = sm_count() / 2;
   if (clusters > total) clusters = total;
-  gemm2_kernel<<<2 * clusters, kThreads, Gemm2Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  gemm2_kernel<<<2 * clusters, kThreads, Gemm2Cfg::kSmemBytes, stream>>>(tmA0, tmB0, p0, tmA1, tmB1, p1, tiles1);
   SIMVGB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -113,13 +113,9 @@ def _stream():
 
 
 # ---------------------------------------------------------------------------------------------- GEMM
-def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, bias=None, out=None, out2=None, res=None,
-         scale=1.0, scale_cols=0, row_scale=None, rows_per_scale=1, k_splits=1, accumulate=False, ldo=None):
-    """C[M,N] = epilogue(A(M,K) @ B(N,K)^T).  A: [M,K] (or [K,M] if a_mn), B: [N,K] (or [K,N] if b_mn), bf16.
-
-    Returns `out` (allocated when None: bf16 for the BF16/GELU epilogues, fp32 otherwise)."""
+def _gemm_args(A, B, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, bias=None, out=None, out2=None, res=None,
+               scale=1.0, scale_cols=0, row_scale=None, rows_per_scale=1, k_splits=1, accumulate=False, ldo=None):
     L.require_device(A)
-    lib = _lib_setup()
     a = L.GemmArgs()
     a.M, a.N, a.K = M, N, K
     a.a_mn_major, a.b_mn_major = int(a_mn), int(b_mn)
@@ -147,10 +143,31 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BF16, bias=None,
     a.rows_per_scale = rows_per_scale
     a.accumulate = int(accumulate)
     fam = "gemm" if not _prof_detail[0] else "gemm M=%d N=%d K=%d a_mn=%d b_mn=%d epi=%d ks=%d" % (M, N, K, a_mn, b_mn, epilogue, k_splits)
-    with _timed(fam, 2.0 * M * N * K):
+    return a, out, fam, 2.0 * M * N * K
+
+
+def gemm(A, B, M, N, K, **kw):
+    """C[M,N] = epilogue(A(M,K) @ B(N,K)^T).  A: [M,K] (or [K,M] if a_mn), B: [N,K] (or [K,N] if b_mn), bf16.
+
+    Returns `out` (allocated when None: bf16 for the BF16/GELU epilogues, fp32 otherwise)."""
+    lib = _lib_setup()
+    a, out, fam, flops = _gemm_args(A, B, M, N, K, **kw)
+    with _timed(fam, flops):
         L.check(lib.simvgb_gemm(ctypes.byref(a), L.c_vp(_stream())), "gemm")
     _launches[0] += 1
     return out
+
+
+def gemm_pair(first, second):
+    """Two independent GEMMs in one persistent launch (simvgb_gemm_pair): `first` / `second` are (A, B, M, N, K, kwargs)
+    tuples with the arguments of gemm().  Used for the vision-expert / text-expert problems of a multiway layer."""
+    lib = _lib_setup()
+    a0, out0, fam, fl0 = _gemm_args(*first[:5], **first[5])
+    a1, out1, _, fl1 = _gemm_args(*second[:5], **second[5])
+    with _timed(fam, fl0 + fl1):
+        L.check(lib.simvgb_gemm_pair(ctypes.byref(a0), ctypes.byref(a1), L.c_vp(_stream())), "gemm_pair")
+    _launches[0] += 1
+    return out0, out1
 
 
 def wgrad_splits(M, N, K):
@@ -159,6 +176,18 @@ def wgrad_splits(M, N, K):
     tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
     kb = (K + 63) // 64
     return max(1, min((2 * 148 + tiles - 1) // tiles, kb // 32))
+
+
+def _wgrad_spec(dY, X, Dout, Din, R, out):
+    ks = wgrad_splits(Dout, Din, R)
+    if ks == 1:
+        return (dY, X, Dout, Din, R, dict(a_mn=True, b_mn=True, epilogue=EPI_F32, out=out, accumulate=True))
+    return (dY, X, Dout, Din, R, dict(a_mn=True, b_mn=True, epilogue=EPI_ATOMIC, out=out, k_splits=ks))
+
+
+def wgrad_pair(first, second):
+    """Two weight-gradient GEMMs (dY, X, Dout, Din, R, out) in one launch."""
+    return gemm_pair(_wgrad_spec(*first), _wgrad_spec(*second))
 
 
 def wgrad(dY, X, Dout, Din, R, out=None):

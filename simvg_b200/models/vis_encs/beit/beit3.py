@@ -315,30 +315,47 @@ def encoder_forward(mod, image, ids, pad_mask, save):
          K.embed_text(glob["text_embed"][0], ids, pad_u8, glob["posB"][0], B, Lt, D)]
     dps = _drop_path_scales(mod, B, image.device)
     saved = []
+    scale_q = (D // H) ** -0.5
     for li, pair in enumerate(layers):
         dp1, dp2 = dps[li]
+        dpv = (dp1, dp2)
         sv = [dict(), dict()]
-        qkv = [None, None]
+        # Every projection is one launch for BOTH experts (K.gemm_pair): the text problem (B*Lt rows) rides in the tail of
+        # the vision problem's persistent grid instead of paying its own launch + ramp.
+        h, st1 = [None, None], [None, None]
         for g, G in enumerate(pair):
-            h, m1, r1 = K.ln_fwd(x[g], G.w["ln1_w"], G.w["ln1_b"], eps)
-            qkv[g] = K.gemm(h, G.Wqkv, Rs[g], 3 * D, D, epilogue=K.EPI_BF16, bias=G.bqkv, scale=(D // H) ** -0.5, scale_cols=D)
-            sv[g].update(x_in=x[g], h=h, m1=m1, r1=r1, qkv=qkv[g])
+            h[g], m1, r1 = K.ln_fwd(x[g], G.w["ln1_w"], G.w["ln1_b"], eps)
+            st1[g] = (m1, r1)
+        qkv = K.gemm_pair(*[(h[g], G.Wqkv, Rs[g], 3 * D, D, dict(epilogue=K.EPI_BF16, bias=G.bqkv, scale=scale_q, scale_cols=D))
+                            for g, G in enumerate(pair)])
+        for g in range(2):
+            sv[g].update(x_in=x[g], h=h[g], m1=st1[g][0], r1=st1[g][1], qkv=qkv[g])
         o_v, o_t, lse = K.attn_fwd(qkv[0], qkv[1], pad_u8, B, H, Lv, Lt)
         o = (o_v, o_t)
+        a, sti = [None, None], [None, None]
         for g, G in enumerate(pair):
-            a, mi, ri = K.ln_fwd(o[g], G.w["in_w"], G.w["in_b"], eps)
-            xmid = K.gemm(a, G.wb["o_w"], Rs[g], D, D, epilogue=K.EPI_RESID, bias=G.w["o_b"], res=x[g], row_scale=dp1,
-                          rows_per_scale=Ls[g])
-            h2, m2, r2 = K.ln_fwd(xmid, G.w["ln2_w"], G.w["ln2_b"], eps)
-            # fc1 + bias; the exact-erf GELU is applied inside the FFN LayerNorm kernel (LN_F(gelu(u))) and recomputed in the
-            # backward, so the activation itself is never written to HBM.
-            u = K.gemm(h2, G.wb["fc1_w"], Rs[g], F, D, epilogue=K.EPI_BF16, bias=G.w["fc1_b"])
-            f, mf, rf = K.ln_fwd(u, G.w["fl_w"], G.w["fl_b"], eps, gelu=True)
-            xn = K.gemm(f, G.wb["fc2_w"], Rs[g], D, F, epilogue=K.EPI_RESID, bias=G.w["fc2_b"], res=xmid, row_scale=dp2,
-                        rows_per_scale=Ls[g])
+            a[g], mi, ri = K.ln_fwd(o[g], G.w["in_w"], G.w["in_b"], eps)
+            sti[g] = (mi, ri)
+        xmid = K.gemm_pair(*[(a[g], G.wb["o_w"], Rs[g], D, D, dict(epilogue=K.EPI_RESID, bias=G.w["o_b"], res=x[g], row_scale=dpv[0],
+                                                               rows_per_scale=Ls[g])) for g, G in enumerate(pair)])
+        h2, st2 = [None, None], [None, None]
+        for g, G in enumerate(pair):
+            h2[g], m2, r2 = K.ln_fwd(xmid[g], G.w["ln2_w"], G.w["ln2_b"], eps)
+            st2[g] = (m2, r2)
+        # fc1 + bias; the exact-erf GELU is applied inside the FFN LayerNorm kernel (LN_F(gelu(u))) and recomputed in the
+        # backward, so the activation itself is never written to HBM.
+        u = K.gemm_pair(*[(h2[g], G.wb["fc1_w"], Rs[g], F, D, dict(epilogue=K.EPI_BF16, bias=G.w["fc1_b"])) for g, G in enumerate(pair)])
+        f, stf = [None, None], [None, None]
+        for g, G in enumerate(pair):
+            f[g], mf, rf = K.ln_fwd(u[g], G.w["fl_w"], G.w["fl_b"], eps, gelu=True)
+            stf[g] = (mf, rf)
+        xn = K.gemm_pair(*[(f[g], G.wb["fc2_w"], Rs[g], D, F, dict(epilogue=K.EPI_RESID, bias=G.w["fc2_b"], res=xmid[g], row_scale=dpv[1],
+                                                             rows_per_scale=Ls[g])) for g, G in enumerate(pair)])
+        for g in range(2):
             if save:
-                sv[g].update(o=o[g], a=a, mi=mi, ri=ri, xmid=xmid, h2=h2, m2=m2, r2=r2, u=u, f=f, mf=mf, rf=rf)
-            x[g] = xn
+                sv[g].update(o=o[g], a=a[g], mi=sti[g][0], ri=sti[g][1], xmid=xmid[g], h2=h2[g], m2=st2[g][0], r2=st2[g][1],
+                             u=u[g], f=f[g], mf=stf[g][0], rf=stf[g][1])
+            x[g] = xn[g]
         if save:
             saved.append(dict(g=sv, lse=lse, dp=(dp1, dp2)))
     outs, fin = [], []
@@ -379,44 +396,48 @@ def encoder_backward(mod, ctx, dxv, dxt):
     for li in range(nl - 1, -1, -1):
         sl = ctx["layers"][li]
         dp1, _dp2 = sl["dp"]
-        dO = [None, None]
-        for g, G in enumerate(layers[li]):
-            sv = sl["g"][g]
-            R = Rs[g]
-            # ---- FFN:  x = xmid + dp2 * fc2(LN_F(gelu(fc1(LN2(xmid)))))
-            K.wgrad(dyb[g], sv["f"], D, F, R, out=G.g["fc2_w"])
-            df = K.gemm(dyb[g], G.wb["fc2_w"], R, F, D, b_mn=True, epilogue=K.EPI_BF16)
-            du = torch.empty(R, F, device=dev, dtype=bf16)
-            K.ln_bwd(2, None, df, G.w["fl_w"], sv["mf"], sv["rf"], G.g["fl_w"], G.g["fl_b"], dx=du, u=sv["u"],
+        Gs = layers[li]
+        svs = sl["g"]
+        # ---- FFN:  x = xmid + dp2 * fc2(LN_F(gelu(fc1(LN2(xmid)))))      (each GEMM: both experts in one launch)
+        K.wgrad_pair(*[(dyb[g], svs[g]["f"], D, F, Rs[g], Gs[g].g["fc2_w"]) for g in range(2)])
+        df = K.gemm_pair(*[(dyb[g], Gs[g].wb["fc2_w"], Rs[g], F, D, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
+        du = [torch.empty(Rs[g], F, device=dev, dtype=bf16) for g in range(2)]
+        for g, G in enumerate(Gs):
+            K.ln_bwd(2, None, df[g], G.w["fl_w"], svs[g]["mf"], svs[g]["rf"], G.g["fl_w"], G.g["fl_b"], dx=du[g], u=svs[g]["u"],
                      dbias_prev=G.g["fc1_b"])
-            del df
-            K.wgrad(du, sv["h2"], F, D, R, out=G.g["fc1_w"])
-            dh2 = K.gemm(du, G.wb["fc1_w"], R, D, F, b_mn=True, epilogue=K.EPI_BF16)
-            del du
-            K.ln_bwd(0, sv["xmid"], dh2, G.w["ln2_w"], sv["m2"], sv["r2"], G.g["ln2_w"], G.g["ln2_b"], dres_in=dres[g],
+        del df
+        K.wgrad_pair(*[(du[g], svs[g]["h2"], F, D, Rs[g], Gs[g].g["fc1_w"]) for g in range(2)])
+        dh2 = K.gemm_pair(*[(du[g], Gs[g].wb["fc1_w"], Rs[g], D, F, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
+        del du
+        for g, G in enumerate(Gs):
+            K.ln_bwd(0, svs[g]["xmid"], dh2[g], G.w["ln2_w"], svs[g]["m2"], svs[g]["r2"], G.g["ln2_w"], G.g["ln2_b"], dres_in=dres[g],
                      dres_out=dres[g], dyb=dyb[g], row_scale=dp1, rows_per_scale=Ls[g], dbias_prev=G.g["o_b"])
-            # ---- attention output:  xmid = x_in + dp1 * out_proj(LN_inner(O))
-            K.wgrad(dyb[g], sv["a"], D, D, R, out=G.g["o_w"])
-            da = K.gemm(dyb[g], G.wb["o_w"], R, D, D, b_mn=True, epilogue=K.EPI_BF16)
-            dO[g] = torch.empty(R, D, device=dev, dtype=bf16)
-            K.ln_bwd(1, sv["o"], da, G.w["in_w"], sv["mi"], sv["ri"], G.g["in_w"], G.g["in_b"], dx=dO[g])
-        svv, svt = sl["g"]
+        del dh2
+        # ---- attention output:  xmid = x_in + dp1 * out_proj(LN_inner(O))
+        K.wgrad_pair(*[(dyb[g], svs[g]["a"], D, D, Rs[g], Gs[g].g["o_w"]) for g in range(2)])
+        da = K.gemm_pair(*[(dyb[g], Gs[g].wb["o_w"], Rs[g], D, D, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
+        dO = [torch.empty(Rs[g], D, device=dev, dtype=bf16) for g in range(2)]
+        for g, G in enumerate(Gs):
+            K.ln_bwd(1, svs[g]["o"], da[g], G.w["in_w"], svs[g]["mi"], svs[g]["ri"], G.g["in_w"], G.g["in_b"], dx=dO[g])
+        del da
+        svv, svt = svs
         dqkv = K.attn_bwd(svv["qkv"], svt["qkv"], ctx["pad"], svv["o"], svt["o"], sl["lse"], dO[0], dO[1], B, H, Lv, Lt,
                           ws=mod._attn_ws)
-        for g, G in enumerate(layers[li]):
-            sv = sl["g"][g]
-            R = Rs[g]
+        for g, G in enumerate(Gs):
             K.colsum(dqkv[g], out=G.gbqkv)
-            K.wgrad(dqkv[g], sv["h"], 3 * D, D, R, out=G.gWqkv)
-            dh = K.gemm(dqkv[g], G.Wqkv, R, D, 3 * D, b_mn=True, epilogue=K.EPI_BF16)
+        K.wgrad_pair(*[(dqkv[g], svs[g]["h"], 3 * D, D, Rs[g], Gs[g].gWqkv) for g in range(2)])
+        dh = K.gemm_pair(*[(dqkv[g], Gs[g].Wqkv, Rs[g], D, 3 * D, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
+        for g, G in enumerate(Gs):
+            sv = svs[g]
             if li > 0:
                 Gp = layers[li - 1][g]
-                K.ln_bwd(0, sv["x_in"], dh, G.w["ln1_w"], sv["m1"], sv["r1"], G.g["ln1_w"], G.g["ln1_b"], dres_in=dres[g],
+                K.ln_bwd(0, sv["x_in"], dh[g], G.w["ln1_w"], sv["m1"], sv["r1"], G.g["ln1_w"], G.g["ln1_b"], dres_in=dres[g],
                          dres_out=dres[g], dyb=dyb[g], row_scale=ctx["layers"][li - 1]["dp"][1], rows_per_scale=Ls[g],
                          dbias_prev=Gp.g["fc2_b"])
             else:
-                K.ln_bwd(0, sv["x_in"], dh, G.w["ln1_w"], sv["m1"], sv["r1"], G.g["ln1_w"], G.g["ln1_b"], dres_in=dres[g],
+                K.ln_bwd(0, sv["x_in"], dh[g], G.w["ln1_w"], sv["m1"], sv["r1"], G.g["ln1_w"], G.g["ln1_b"], dres_in=dres[g],
                          dres_out=dres[g])
+        del dh
         ctx["layers"][li] = None  # release this layer's activations
         if ddp is not None and li > 0:
             # every gradient of layer li is final now (its fc2 bias was written by layer li+1's LN1 backward)

@@ -45,6 +45,36 @@ def test_gemm_all_operand_majors(K, M, N, K_):
         assert maxrel(out, ref) < 1e-5
 
 
+def test_gemm_pair_equals_two_gemms(K):
+    """simvgb_gemm_pair: the vision-expert and text-expert problems of one layer in a single persistent launch — different
+    M, operand majors, epilogues and split-K factors — must equal two separate launches bit for bit (same tile schedule per
+    problem, deterministic epilogues) and fall back cleanly when one problem is not eligible for the 2-CTA kernel."""
+    torch.manual_seed(4)
+    Mv, Mt, N, K_ = 3000, 520, 768, 768
+    Xv, Xt = torch.randn(Mv, K_, device=DEV).bfloat16(), torch.randn(Mt, K_, device=DEV).bfloat16()
+    Wv, Wt = torch.randn(N, K_, device=DEV).bfloat16(), torch.randn(N, K_, device=DEV).bfloat16()
+    bv, bt = torch.randn(N, device=DEV), torch.randn(N, device=DEV)
+    rv, rt = torch.randn(Mv, N, device=DEV), torch.randn(Mt, N, device=DEV)
+    # forward-style: bf16 output with bias / scale, and residual epilogue
+    for kw_v, kw_t in ((dict(epilogue=K.EPI_BF16, bias=bv, scale=0.125, scale_cols=256), dict(epilogue=K.EPI_BF16, bias=bt, scale=0.125, scale_cols=256)),
+                       (dict(epilogue=K.EPI_RESID, bias=bv, res=rv), dict(epilogue=K.EPI_RESID, bias=bt, res=rt)),
+                       (dict(epilogue=K.EPI_F32), dict(epilogue=K.EPI_BF16, b_mn=True))):
+        Wt_use = Wt.t().contiguous() if kw_t.get("b_mn") else Wt
+        pv, pt = K.gemm_pair((Xv, Wv, Mv, N, K_, kw_v), (Xt, Wt_use, Mt, N, K_, kw_t))
+        sv, st = K.gemm(Xv, Wv, Mv, N, K_, **kw_v), K.gemm(Xt, Wt_use, Mt, N, K_, **kw_t)
+        assert torch.equal(pv, sv) and torch.equal(pt, st)
+    # weight-gradient style: MN-major operands, split-K atomics for the long problem, plain accumulate for the short one
+    dYv, dYt = torch.randn(Mv, N, device=DEV).bfloat16(), torch.randn(Mt, N, device=DEV).bfloat16()
+    gv, gt = torch.zeros(N, K_, device=DEV), torch.zeros(N, K_, device=DEV)
+    K.wgrad_pair((dYv, Xv, N, K_, Mv, gv), (dYt, Xt, N, K_, Mt, gt))
+    assert maxrel(gv, dYv.float().t() @ Xv.float()) < 1e-5
+    assert maxrel(gt, dYt.float().t() @ Xt.float()) < 1e-5
+    # one problem too narrow for the 2-CTA kernel (N <= 128): two launches behind the same call
+    Wn = torch.randn(72, K_, device=DEV).bfloat16()
+    pv, pn = K.gemm_pair((Xv, Wv, Mv, N, K_, dict(epilogue=K.EPI_F32)), (Xt, Wn, Mt, 72, K_, dict(epilogue=K.EPI_F32)))
+    assert maxrel(pv, Xv.float() @ Wv.float().t()) < 1e-5 and maxrel(pn, Xt.float() @ Wn.float().t()) < 1e-5
+
+
 def test_gemm_epilogues(K):
     torch.manual_seed(1)
     M, N, K_ = 1000, 768, 768
