@@ -331,10 +331,10 @@ def run_ours(args, cfg_name):
         n, tot_ms, fl = prof[fam]
         ach = fl / (tot_ms * 1e-3) / 1e12
         # DRAM traffic of the family's largest launch from the committed ncu --set full capture (profiles/r01_gemm_ncu.md):
-        # QKV forward GEMM 102464x2304x768: 581.4 MB read+write vs 633.1 MB algorithmic.
-        traffic = 581.4e6 if (fam == "gemm" and cfg_name == "cfg2") else None
+        # QKV forward GEMM pair (vision 102464x2304x768 + text 1280x2304x768): 597.5 MB read+write vs 644.5 MB algorithmic.
+        traffic = 597.5e6 if (fam == "gemm" and cfg_name == "cfg2") else None
         roofline = {"bound": "tensor", "kernel": fam, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                    "traffic": traffic, "traffic_note": "bytes/launch of the largest launch (QKV fwd GEMM), ncu capture in profiles/r01_gemm_ncu.md; algorithmic 633.1e6",
+                    "traffic": traffic, "traffic_note": "bytes/launch of the largest launch (QKV fwd GEMM, both experts), ncu capture in profiles/r01_gemm_ncu.md; algorithmic 644.5e6",
                     "launches": n, "avg_ms": tot_ms / n, "peak_source": peak_src,
                     "families": {k: {"launches": v[0], "ms": v[1], "tflops": v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None}
                                  for k, v in prof.items()}}
