@@ -443,9 +443,16 @@ __global__ void __launch_bounds__(128) ln_bwd_warp_kernel(const LnBwdParams p) {
 // Wide rows (FFN LayerNorm + GELU backward, C = 3072 / 4096): one 128-thread block per row, each warp owns a contiguous
 // quarter of the columns (NCH chunks of 8 per lane, register accumulators), one block barrier per row (double-buffered
 // partials), next row's packed operands prefetched.  Blocks are small and independent, so several rows are in flight per SM.
+constexpr int kWideStages = 3;   // rows of dy / u in flight per block (bulk-copied into shared memory)
 template <int NCH>
 __global__ void __launch_bounds__(128) ln_bwd_wide_kernel(const LnBwdParams p) {
   constexpr int C = NCH * 4 * 256;
+  // dy and u rows are streamed through a kWideStages-deep shared-memory ring with cp.async.bulk (TMA): with register
+  // prefetch of one row, two resident 252-register blocks keep only ~24 KB in flight per SM (3.3 TB/s); the ring keeps
+  // kWideStages x 2 x C x 2 bytes per block in flight independent of the register budget.
+  extern __shared__ __align__(128) uint8_t wide_smem[];
+  bf16* ring = reinterpret_cast<bf16*>(wide_smem);                                   // [kWideStages][2][C]
+  uint64_t* full = reinterpret_cast<uint64_t*>(wide_smem + kWideStages * 2 * C * 2);   // [kWideStages]
   __shared__ float red[2][4][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col0 = warp * NCH * 256 + lane * 8;
@@ -456,28 +463,35 @@ __global__ void __launch_bounds__(128) ln_bwd_wide_kernel(const LnBwdParams p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { acc_g[c][i] = 0.f; acc_b[c][i] = 0.f; acc_p[c][i] = 0.f; }
   }
-  uint4 ndy[NCH], nu[NCH];
-  float nmu = 0.f, nrs = 0.f;
-  auto prefetch = [&](long long row) {
+  auto issue = [&](long long row, int stage) {   // thread 0 only
     if (row < p.R) {
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const long long off = row * C + col0 + c * 256;
-        ndy[c] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.dy) + off));
-        nu[c] = __ldg(reinterpret_cast<const uint4*>(p.u + off));
-      }
-      nmu = __ldg(p.mean + row);
-      nrs = __ldg(p.rstd + row);
+      mbar_expect_tx(&full[stage], 2 * C * 2);
+      bulk_g2s(ring + (stage * 2 + 0) * C, reinterpret_cast<const bf16*>(p.dy) + row * C, C * 2, &full[stage]);
+      bulk_g2s(ring + (stage * 2 + 1) * C, p.u + row * C, C * 2, &full[stage]);
     }
   };
-  prefetch(blockIdx.x);
-  int par = 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWideStages; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWideStages; ++s) issue(blockIdx.x + (long long)s * gridDim.x, s);
+  }
+  float nmu = 0.f, nrs = 0.f;
+  if (blockIdx.x < p.R) { nmu = __ldg(p.mean + blockIdx.x); nrs = __ldg(p.rstd + blockIdx.x); }
+  int par = 0, stage = 0;
+  uint32_t phase = 0;
   for (long long row = blockIdx.x; row < p.R; row += gridDim.x, par ^= 1) {
+    const float mu = nmu, rs = nrs;
+    if (row + gridDim.x < p.R) { nmu = __ldg(p.mean + row + gridDim.x); nrs = __ldg(p.rstd + row + gridDim.x); }
+    mbar_wait(&full[stage], phase);
     uint4 cdy[NCH], cu[NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) { cdy[c] = ndy[c]; cu[c] = nu[c]; }
-    const float mu = nmu, rs = nrs;
-    prefetch(row + gridDim.x);
+    for (int c = 0; c < NCH; ++c) {
+      cdy[c] = *reinterpret_cast<const uint4*>(ring + (stage * 2 + 0) * C + col0 + c * 256);
+      cu[c] = *reinterpret_cast<const uint4*>(ring + (stage * 2 + 1) * C + col0 + c * 256);
+    }
     float xh[NCH][8], dyg[NCH][8], gg[NCH][8];
     float s1 = 0.f, s2 = 0.f;
     float2 s1v = make_float2(0.f, 0.f), s2v = make_float2(0.f, 0.f);
@@ -509,7 +523,9 @@ __global__ void __launch_bounds__(128) ln_bwd_wide_kernel(const LnBwdParams p) {
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
     if (lane == 0) { red[par][warp][0] = s1; red[par][warp][1] = s2; }
-    __syncthreads();
+    __syncthreads();   // also: every thread has read this ring stage
+    if (threadIdx.x == 0) issue(row + (long long)kWideStages * gridDim.x, stage);
+    if (++stage == kWideStages) { stage = 0; phase ^= 1; }
     const float c1 = (red[par][0][0] + red[par][1][0] + red[par][2][0] + red[par][3][0]) * (1.0f / C);
     const float c2 = (red[par][0][1] + red[par][1][1] + red[par][2][1] + red[par][3][1]) * (1.0f / C);
     const float2 nc1 = splat2(-c1), nc2 = splat2(-c2);
@@ -769,8 +785,15 @@ extern "C" int simvgb_ln_bwd(const simvgb_ln_bwd_args* a, void* stream) {
     long long blocks = p.R;
     const long long cap = (long long)sm_count() * 2;   // 255 registers x 128 threads: two resident blocks per SM
     if (blocks > cap) blocks = cap;
-    if (p.C == 3072) ln_bwd_wide_kernel<3><<<(unsigned)blocks, 128, 0, st>>>(p);
-    else ln_bwd_wide_kernel<4><<<(unsigned)blocks, 128, 0, st>>>(p);
+    const size_t ring_bytes = (size_t)kWideStages * 2 * p.C * 2 + kWideStages * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+      SIMVGB_CUDA(cudaFuncSetAttribute(ln_bwd_wide_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2 * 3072 * 2 + 64));
+      SIMVGB_CUDA(cudaFuncSetAttribute(ln_bwd_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2 * 4096 * 2 + 64));
+      attr_set = true;
+    }
+    if (p.C == 3072) ln_bwd_wide_kernel<3><<<(unsigned)blocks, 128, ring_bytes, st>>>(p);
+    else ln_bwd_wide_kernel<4><<<(unsigned)blocks, 128, ring_bytes, st>>>(p);
     SIMVGB_CUDA(cudaGetLastError());
     return 0;
   }
