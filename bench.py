@@ -3,9 +3,10 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg4|cfg5|ref32]
 
-Workload (BASELINE.json configs[1], the one `metric` is quoted on): ViT-B/16 BEiT-3 encoder + 3-layer object-token decoder
-(the reference's shipped depth; --dec-layers 6 for the head default), 640x640, bs=64 per GPU, synthetic RefCOCO-shaped
-inputs, random-init weights.  One "step" = one optimiser step on one batch.
+Workload (BASELINE.json configs[1], the one `metric` is quoted on): ViT-B/16 BEiT-3 encoder + 6-layer object-token decoder
+(as BASELINE.json names it — the head's constructor default, tgqs_kd_detr_head.py:24-48; the reference's shipped RefCOCO
+configs set 3: --dec-layers 3), 640x640, bs=64 per GPU, synthetic RefCOCO-shaped inputs, random-init weights.
+One "step" = one optimiser step on one batch.
 
   value  : whole-job img/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e    : the same metric through the public plugin API with HOST (pinned) inputs: every step copies its inputs
@@ -28,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     #        vit      img  patch  bs  dec_layers branch_loss_weight
-    "cfg2": ("base", 640, 16, 64, 3, {"decoder": 1.0, "balanced_distill": {"token": 2.0, "distill": 1.0}}),
+    "cfg2": ("base", 640, 16, 64, 6, {"decoder": 1.0, "balanced_distill": {"token": 2.0, "distill": 1.0}}),
     "cfg3": ("large", 640, 16, 32, 3, {"decoder": 1.0, "balanced_distill": {"token": 1.0, "distill": 0.4}}),
     "cfg4": ("large", 768, 16, 16, 3, {"decoder": 1.0, "balanced_distill": {"token": 1.0, "distill": 0.4}}),
     "cfg5": ("large", 640, 16, 64, 3, {"decoder": 1.0}),
