@@ -237,3 +237,36 @@ def test_head_cpu_forward_matches_oracle_small():
     assert torch.allclose(out["outputs_coord_decoder_branch"], oo["outputs_coord_decoder_branch"], atol=1e-5)
     assert torch.allclose(out["outputs_coord_token_branch"], oo["outputs_coord_token_branch"], atol=1e-5)
     assert T._BIG_ROWS > 0
+
+
+def test_absorbed_cross_attention_equals_projected_path():
+    """The decoder's few-queries-vs-long-memory attention absorbs the key/value projections into the query/output side.  It is
+    a reassociation of nn.MultiheadAttention's arithmetic: outputs and every gradient must match the projected form."""
+    from simvg_b200.models.heads.tgqs_kd_detr_head import transformer as T
+    torch.manual_seed(11)
+    B, nq, nk, E, H = 3, 2, 300, 64, 4
+    att = T._Attention(E, H, 0.0).double()
+    with torch.no_grad():
+        att.attn.in_proj_bias.normal_(0, 0.3)
+        att.attn.out_proj.bias.normal_(0, 0.3)
+    mask = torch.zeros(B, nk, dtype=torch.bool)
+    mask[1, 250:] = True
+    res = []
+    for min_keys in (10 ** 9, 1):
+        old = T._ABSORB_MIN_KEYS
+        T._ABSORB_MIN_KEYS = min_keys
+        try:
+            g = torch.Generator().manual_seed(5)
+            q = torch.randn(B, nq, E, generator=g, dtype=torch.double, requires_grad=True)
+            mem = torch.randn(B, nk, E, generator=g, dtype=torch.double, requires_grad=True)
+            qpos = torch.randn(B, nq, E, generator=g, dtype=torch.double)
+            kpos = torch.randn(B, nk, E, generator=g, dtype=torch.double)
+            att.zero_grad()
+            out = att(q, mem, mem, query_pos=qpos, key_pos=kpos, key_padding_mask=mask)
+            (out * torch.randn(out.shape, generator=g, dtype=torch.double)).sum().backward()
+            res.append((out.detach(), q.grad, mem.grad, att.attn.in_proj_weight.grad.clone(), att.attn.in_proj_bias.grad.clone(),
+                        att.attn.out_proj.weight.grad.clone()))
+        finally:
+            T._ABSORB_MIN_KEYS = old
+    for a, b in zip(*res):
+        assert torch.allclose(a, b, rtol=1e-9, atol=1e-11)
