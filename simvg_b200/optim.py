@@ -53,14 +53,19 @@ class FusedAdamAMSGrad:
             s.fb.attach_grads()
         self._sumsq = None
         self._hyper = None        # device [n_segments, 4]: lr, 1 - beta1^t, sqrt(1 - beta2^t), pad  (graph mode)
-        self._hyper_host = None   # pinned mirror
         self.graph_mode = False
 
-    # ---- CUDA-graph support: step-dependent scalars live in device memory, refreshed by advance() before each replay
+    # ---- CUDA-graph support: the step-dependent scalars live in device memory and are advanced BY THE GRAPH ITSELF
+    # (beta^t is a running product updated by a tiny in-graph op), so replays need no per-step host->device traffic and the
+    # host may run any number of steps ahead of the device.
     def enable_graph_mode(self):
         dev = self.segments[0].fb.data.device
-        self._hyper = torch.zeros(len(self.segments), 4, device=dev, dtype=torch.float32)
-        self._hyper_host = torch.zeros(len(self.segments), 4, dtype=torch.float32).pin_memory()
+        n = len(self.segments)
+        self._hyper = torch.zeros(n, 4, device=dev, dtype=torch.float32)       # lr, 1 - beta1^t, sqrt(1 - beta2^t), pad
+        self._betas_dev = torch.tensor([self.betas[0], self.betas[1]], device=dev, dtype=torch.float64)
+        self._pow = torch.tensor([self.betas[0] ** self.t, self.betas[1] ** self.t], device=dev, dtype=torch.float64)
+        self._lr_host = [s.lr for s in self.segments]
+        self._lr_dev = torch.tensor(self._lr_host, device=dev, dtype=torch.float32)
         self.graph_mode = True
         for s in self.segments:
             s.ensure_state()
@@ -68,13 +73,13 @@ class FusedAdamAMSGrad:
             self._sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
 
     def advance(self):
-        """Graph mode: t += 1 and upload this step's {lr, bias corrections} (async, on the current stream)."""
+        """Graph mode, once per step before the replay: host-side step count; learning rates are re-uploaded only when a
+        scheduler changed them (a blocking 8-byte copy, outside the graph)."""
         self.t += 1
-        for i, s in enumerate(self.segments):
-            self._hyper_host[i, 0] = s.lr
-            self._hyper_host[i, 1] = 1.0 - self.betas[0] ** self.t
-            self._hyper_host[i, 2] = (1.0 - self.betas[1] ** self.t) ** 0.5
-        self._hyper.copy_(self._hyper_host, non_blocking=True)
+        lrs = [s.lr for s in self.segments]
+        if lrs != self._lr_host:
+            self._lr_host = lrs
+            self._lr_dev.copy_(torch.tensor(lrs, dtype=torch.float32))
 
     @property
     def param_groups(self):  # scheduler-facing view (core/scheduler.py multiplies group["lr"])
@@ -107,6 +112,10 @@ class FusedAdamAMSGrad:
     def _step_graph(self):
         """Same update with step-invariant launch arguments (advance() must have been called for this step)."""
         clip = float(self.grad_norm_clip) if self.grad_norm_clip else 0.0
+        self._pow.mul_(self._betas_dev)                                   # beta^t (fp64 running product, on the device)
+        self._hyper[:, 0] = self._lr_dev
+        self._hyper[:, 1] = (1.0 - self._pow[0]).float()
+        self._hyper[:, 2] = (1.0 - self._pow[1]).sqrt().float()
         if clip > 0:
             self._sumsq.zero_()
             for s in self.segments:
