@@ -201,6 +201,8 @@ def run_ours(args, cfg_name):
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout: keep stdout to the one JSON line
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
