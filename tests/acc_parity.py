@@ -3,7 +3,7 @@ arithmetic) from IDENTICAL weights on IDENTICAL batches, then evaluate both on t
 
 Task: the box is recoverable from the image — a bright rectangle on N(0, 0.3^2) noise at the ground-truth box; text tokens are
 random.  Stochastic layers are off (eval-mode forward with losses, as in smoke()) so the two runs are comparable step by step.
-Writes gpurun_out/acc_parity.json.   python tools/acc_parity.py [steps] [batch] [img_size]
+Writes gpurun_out/acc_parity.json.   python tests/acc_parity.py [steps] [batch] [img_size]
 """
 import copy
 import json
@@ -14,7 +14,7 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import simvg_oracle as O  # noqa: E402  (checker: this tool is test infrastructure)
+from oracle import simvg_oracle as O  # noqa: E402  (checker: lives under tests/ because only tests may use the oracle)
 from simvg_b200.models import build_model  # noqa: E402
 from simvg_b200.optim import FusedAdamAMSGrad  # noqa: E402
 from tools.synth import make_batch, model_cfg  # noqa: E402
