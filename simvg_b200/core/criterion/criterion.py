@@ -127,25 +127,33 @@ class SetCriterion(nn.Module):
             num_boxes = torch.clamp(nb / get_world_size(), min=1.0)[0]
         else:
             num_boxes = max(num_boxes, 1.0)
-        tcls = targets.labels.view(-1, 1)
+        # Main output and every auxiliary decoder layer in ONE batched expression ([Ld, B, ...]): with a 6-layer decoder the
+        # per-layer evaluation was 18 x ~75 tiny forward/backward launches per step; the per-layer loss entries of the
+        # returned dict are 0-dim views of the [Ld] results.
+        aux = outputs.get("aux_outputs", [])
+        layers_logits = [a_["pred_logits"] for a_ in aux] + [outputs["pred_logits"]]
+        layers_boxes = [a_["pred_boxes"] for a_ in aux] + [outputs["pred_boxes"]]
+        logits = torch.stack(layers_logits)[:, :, 0]          # [Ld, B, C]
+        src = torch.stack(layers_boxes)[:, :, 0]              # [Ld, B, 4]
+        Ld, Bn, C = logits.shape
+        tcls = targets.labels.view(-1)
         tbox = targets.boxes
-
-        def one(logits, boxes, suffix):
-            if self.loss_class_type == "ce_loss":
-                lc = F.cross_entropy(logits.transpose(1, 2), tcls, self.empty_weight)
-            else:  # weighted_ce_loss with every query matched: per-query weight 1 (criterion.py:128-137)
-                lc = F.cross_entropy(logits.transpose(1, 2), tcls, self.empty_weight, reduction="none").mean(-1).sum()
-            src = boxes[:, 0]
-            l1 = F.l1_loss(src, tbox, reduction="none")
-            giou = 1 - aligned_iou_giou(box_cxcywh_to_xyxy(src), box_cxcywh_to_xyxy(tbox))[1]
-            if self.loss_class_type == "weighted_ce_loss":
-                l1 = l1.sum(-1) * targets.weight
-                giou = giou * targets.weight
-            return {"loss_class" + suffix: lc, "loss_bbox" + suffix: l1.sum() / num_boxes, "loss_giou" + suffix: giou.sum() / num_boxes}
-
-        losses = one(outputs["pred_logits"], outputs["pred_boxes"], "")
-        for i, aux in enumerate(outputs.get("aux_outputs", [])):
-            losses.update(one(aux["pred_logits"], aux["pred_boxes"], "_%d" % i))
+        ce = F.cross_entropy(logits.reshape(Ld * Bn, C), tcls.repeat(Ld), self.empty_weight, reduction="none").view(Ld, Bn)
+        if self.loss_class_type == "ce_loss":                 # weighted mean over the batch (criterion.py:127)
+            lc = ce.sum(1) / self.empty_weight[tcls].sum()
+        else:  # weighted_ce_loss with every query matched: per-query weight 1, mean over queries, sum over batch (:128-137)
+            lc = ce.sum(1)
+        l1 = (src - tbox).abs().sum(-1)                       # [Ld, B]
+        giou = 1 - aligned_iou_giou(box_cxcywh_to_xyxy(src), box_cxcywh_to_xyxy(tbox).expand(Ld, Bn, 4))[1]
+        if self.loss_class_type == "weighted_ce_loss":
+            l1 = l1 * targets.weight
+            giou = giou * targets.weight
+        lb = l1.sum(1) / num_boxes
+        lg = giou.sum(1) / num_boxes
+        lc_l, lb_l, lg_l = lc.unbind(0), lb.unbind(0), lg.unbind(0)
+        losses = {"loss_class": lc_l[-1], "loss_bbox": lb_l[-1], "loss_giou": lg_l[-1]}
+        for i in range(len(aux)):
+            losses.update({"loss_class_%d" % i: lc_l[i], "loss_bbox_%d" % i: lb_l[i], "loss_giou_%d" % i: lg_l[i]})
         return losses
 
     def forward(self, outputs, targets, return_indices=False):
