@@ -280,16 +280,17 @@ class BEIT3(nn.Module):
 
 # ------------------------------------------------------------------------------------------------ kernel sequencing
 def _drop_path_scales(mod, B, device):
-    """Per layer: (attn_scale[B] | None, ffn_scale[B] | None) = Bernoulli(keep)/keep  (timm drop_path, A.8)."""
-    out = []
-    for p in mod.drop_path_probs:
-        if not mod.training or p == 0.0:
-            out.append((None, None))
-        else:
-            keep = 1.0 - p
-            s = [torch.empty(B, device=device, dtype=f32).bernoulli_(keep).div_(keep) for _ in range(2)]
-            out.append((s[0], s[1]))
-    return out
+    """Per layer: (attn_scale[B] | None, ffn_scale[B] | None) = Bernoulli(keep)/keep  (timm drop_path, A.8).
+    All layers are drawn with one bernoulli launch over a [layers, 2, B] keep-probability tensor."""
+    probs = mod.drop_path_probs
+    if not mod.training or not any(p > 0.0 for p in probs):
+        return [(None, None)] * len(probs)
+    keep = getattr(mod, "_dp_keep", None)
+    if keep is None or keep.device != device or keep.shape[2] != B:
+        keep = torch.tensor([1.0 - p for p in probs], dtype=f32).view(-1, 1, 1).expand(len(probs), 2, B).contiguous().to(device)
+        mod._dp_keep = keep
+    s = torch.bernoulli(keep).div_(keep)
+    return [((s[i, 0], s[i, 1]) if p > 0.0 else (None, None)) for i, p in enumerate(probs)]
 
 
 def encoder_forward(mod, image, ids, pad_mask, save):
