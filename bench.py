@@ -259,7 +259,7 @@ def run_ours(args, cfg_name):
     gstep = None
     # world > 1: eager launches.  Capturing the NCCL gradient all-reduces inside the step graph hung at N=2 in round 1
     # (gpurun_out/s2_bench_n2.err) and is left for the next round; the data-parallel path itself is unchanged.
-    if not args.no_graph and world == 1:
+    if not args.no_graph and (world == 1 or args.graph_ddp):
         from simvg_b200.runtime import GraphedTrainStep
         gstep = GraphedTrainStep(model, opt, ddp if world > 1 else None, warmup=max(args.warmup, 3))
 
@@ -388,6 +388,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=2, help="images per CPU-reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch loop instead of the whole-step CUDA graph")
+    ap.add_argument("--graph-ddp", action="store_true", help="experimental: also capture the step graph (with its NCCL all-reduces) when N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, args.config)

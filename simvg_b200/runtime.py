@@ -66,7 +66,11 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         K.reset_launch_count()
-        with torch.cuda.graph(self.graph, stream=side):   # same stream as the warm-up: autograd's AccumulateGrad nodes stay on it
+        # With a process group, NCCL's watchdog thread polls CUDA events while we capture: only this thread's calls may be
+        # policed ("thread_local"), otherwise its cudaEventQuery invalidates the capture.  (Round 1: NCCL capture is still
+        # experimental — bench.py keeps N > 1 on eager launches unless --graph-ddp is given.)
+        mode = "thread_local" if self.ddp is not None else "global"
+        with torch.cuda.graph(self.graph, stream=side, capture_error_mode=mode):   # same stream as the warm-up: autograd's AccumulateGrad nodes stay on it
             losses, preds = self._eager(self.static, metas)
         self.launches_per_step = K.launch_count()
         self.out = (losses, preds)
