@@ -133,8 +133,8 @@ class SetCriterion(nn.Module):
         aux = outputs.get("aux_outputs", [])
         layers_logits = [a_["pred_logits"] for a_ in aux] + [outputs["pred_logits"]]
         layers_boxes = [a_["pred_boxes"] for a_ in aux] + [outputs["pred_boxes"]]
-        logits = torch.stack(layers_logits)[:, :, 0]          # [Ld, B, C]
-        src = torch.stack(layers_boxes)[:, :, 0]              # [Ld, B, 4]
+        logits = torch.stack(layers_logits).squeeze(2)        # [Ld, B, C]   (one query: squeeze is a view, no SelectBackward fill)
+        src = torch.stack(layers_boxes).squeeze(2)            # [Ld, B, 4]
         Ld, Bn, C = logits.shape
         tcls = targets.labels.view(-1)
         tbox = targets.boxes

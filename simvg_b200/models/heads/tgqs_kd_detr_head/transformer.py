@@ -50,14 +50,17 @@ class _Attention(nn.Module):
             k_in = key if key_pos is None else key + key_pos
         E, H = self.embed_dim, self.num_heads
         dh = E // H
-        W, bias = self.attn.in_proj_weight, self.attn.in_proj_bias
+        # q/k/v parts of the packed in_proj parameters as ONE unbind each: three separate slices cost three zero-filled
+        # full-size gradient buffers + copies + accumulations per attention in the backward (~300 launches per step)
+        Wq, Wk, Wv = self.attn.in_proj_weight.view(3, E, E).unbind(0)
+        bq, bk, bv = self.attn.in_proj_bias.view(3, E).unbind(0)
         B, nq, nk = q_in.shape[0], q_in.shape[1], k_in.shape[1]
-        q = F.linear(q_in, W[:E], bias[:E]).view(B, nq, H, dh) * (dh ** -0.5)
+        q = F.linear(q_in, Wq, bq).view(B, nq, H, dh) * (dh ** -0.5)
         if nk >= _ABSORB_MIN_KEYS and nq * H <= 128:
-            o = self._absorbed(q, k_in, value, W, bias, key_padding_mask)
+            o = self._absorbed(q, k_in, value, Wk, bk, Wv, bv, key_padding_mask)
         else:
-            k = _proj(k_in, W[E:2 * E], bias[E:2 * E])
-            v = _proj(value, W[2 * E:], bias[2 * E:])
+            k = _proj(k_in, Wk, bk)
+            v = _proj(value, Wv, bv)
             q = q.transpose(1, 2)
             k = k.view(B, nk, H, dh).transpose(1, 2)
             v = v.view(B, nk, H, dh).transpose(1, 2)
@@ -71,7 +74,7 @@ class _Attention(nn.Module):
         o = F.linear(o, self.attn.out_proj.weight, self.attn.out_proj.bias)
         return identity + o  # proj_drop = 0
 
-    def _absorbed(self, q, k_in, value, W, bias, key_padding_mask):
+    def _absorbed(self, q, k_in, value, Wk, bk, Wv, bv, key_padding_mask):
         """Few queries against a long memory (the object-token decoder: nq = 1..10 queries, N = 1600 image tokens): the key and
         value projections are absorbed into the query / output side, so the [B*N, E] projected keys and values are never formed.
             scores[b,i,h,k] = q[b,i,h] . (Wk_h x_k[b,k] + bk_h) = (Wk_h^T q[b,i,h]) . x_k[b,k] + q[b,i,h] . bk_h
@@ -80,8 +83,8 @@ class _Attention(nn.Module):
         [B*N, E] x [E, E] projections plus their transposes, casts and gradient accumulations (1.9 ms -> ~0.2 ms per layer at cfg2)."""
         B, nq, H, dh = q.shape
         E, nk = self.embed_dim, k_in.shape[1]
-        Wk, bk = W[E:2 * E].view(H, dh, E), bias[E:2 * E].view(H, dh)
-        Wv, bv = W[2 * E:].view(H, dh, E), bias[2 * E:].view(H, dh)
+        Wk, bk = Wk.view(H, dh, E), bk.view(H, dh)
+        Wv, bv = Wv.view(H, dh, E), bv.view(H, dh)
         u = torch.einsum("bihd,hde->bihe", q, Wk).reshape(B, nq * H, E)          # Wk_h^T q
         c = torch.einsum("bihd,hd->bih", q, bk).reshape(B, nq * H, 1)
         s = torch.baddbmm(c, u, k_in.transpose(1, 2))                              # [B, nq*H, nk]
