@@ -170,12 +170,29 @@ def gemm_pair(first, second):
     return out0, out1
 
 
-def wgrad_splits(M, N, K):
-    """Split-K factor for a weight-gradient GEMM (few output tiles, very long K).  Every split pays a full fp32 atomic
-    epilogue for its 128 x 256 tile, so a split must own at least 32 k-blocks (2048 rows) to amortise it."""
-    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
+def wgrad_splits(M, N, K, clusters=74, epi_kb=8):
+    """Split-K factor for a weight-gradient GEMM (few output tiles, very long K).
+
+    2-CTA kernel (N > 128, M >= 256; 256 x 256 tiles on `clusters` = SMs / 2 clusters): minimise
+    waves x (k-blocks per split + epilogue), waves = ceil(tiles * splits / clusters) — the persistent grid runs whole waves, so
+    e.g. 36 tiles x 5 splits = 180 items cost 3 waves where 36 x 2 = 72 items cost one.  Every split keeps >= 32 k-blocks so
+    its fp32 atomic epilogue stays amortised.  Measured on B200 (tools/wgrad_ks_ab.py, K = 102464): 768x3072 ks 5 -> 2:
+    0.437 -> 0.358 ms; 3072x768 0.414 -> 0.363; 2304x768 ks 6 -> 8: 0.336 -> 0.295; 768x768 ks 17 -> 8: 0.119 -> 0.093.
+    1-CTA kernel (narrow N / short M): the earlier rule (about two items per SM)."""
     kb = (K + 63) // 64
-    return max(1, min((2 * 148 + tiles - 1) // tiles, kb // 32))
+    if not (N > 128 and M >= 256):
+        tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
+        return max(1, min((2 * 148 + tiles - 1) // tiles, kb // 32))
+    tiles = ((M + 255) // 256) * ((N + 255) // 256)
+    best_cost, best_ks = None, 1
+    for ks in range(1, max(1, kb // 32) + 1):
+        per = (kb + ks - 1) // ks
+        ks_eff = (kb + per - 1) // per                      # no empty splits (the library applies the same rounding)
+        waves = (tiles * ks_eff + clusters - 1) // clusters
+        cost = waves * (per + epi_kb) + (0.5 * epi_kb if ks_eff > 1 else 0.0)   # atomics cost a little more than plain accumulate
+        if best_cost is None or cost < best_cost - 1e-9:
+            best_cost, best_ks = cost, ks_eff
+    return best_ks
 
 
 def _wgrad_spec(dY, X, Dout, Din, R, out):

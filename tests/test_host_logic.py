@@ -270,3 +270,21 @@ def test_absorbed_cross_attention_equals_projected_path():
             T._ABSORB_MIN_KEYS = old
     for a, b in zip(*res):
         assert torch.allclose(a, b, rtol=1e-9, atol=1e-11)
+
+
+def test_wgrad_split_choice_fills_whole_waves():
+    """Host-side split-K heuristic for the weight-gradient GEMMs (pure Python): the chosen factor keeps >= 32 k-blocks per
+    split and never wastes most of a wave of the 74-cluster persistent grid on the in-step shapes."""
+    from simvg_b200.kernels import wgrad_splits
+    R = 64 * 1601
+    want = {(768, 3072): 2, (3072, 768): 2, (2304, 768): 8, (768, 768): 8}     # measured best on B200 (tools/wgrad_ks_ab.py)
+    for (M, N), ks in want.items():
+        assert wgrad_splits(M, N, R) == ks
+    for M, N, K_ in [(768, 3072, R), (1024, 4096, 32 * 1601), (2304, 768, 1280), (256, 256, 102400), (768, 72, 4096), (100, 768, 640)]:
+        ks = wgrad_splits(M, N, K_)
+        kb = (K_ + 63) // 64
+        assert 1 <= ks <= max(1, kb // 32)
+        if N > 128 and M >= 256 and ks > 1:
+            tiles = ((M + 255) // 256) * ((N + 255) // 256)
+            items = tiles * ks
+            assert items / (74 * ((items + 73) // 74)) > 0.6     # at least 60 % of the last wave's slots are used on average
