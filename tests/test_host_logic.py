@@ -288,3 +288,49 @@ def test_wgrad_split_choice_fills_whole_waves():
             tiles = ((M + 255) // 256) * ((N + 255) // 256)
             items = tiles * ks
             assert items / (74 * ((items + 73) // 74)) > 0.6     # at least 60 % of the last wave's slots are used on average
+
+
+def test_head_absorbed_attention_and_batched_losses_match_oracle():
+    """Head with a 16x16 feature map (256 image tokens: the decoder's cross-attention takes the absorbed-projection form) and
+    a 6-layer decoder (batched auxiliary losses): losses, outputs and the gradient w.r.t. the image features against the oracle."""
+    import copy
+    from oracle import simvg_oracle as O
+    from simvg_b200.models.heads.tgqs_kd_detr_head import transformer as T
+    from simvg_b200.models.heads.tgqs_kd_detr_head.tgqs_kd_detr_head import TextGuidedQuerySelectKDDETRHead
+    from tools.synth import make_batch, model_cfg, synth_state_dict
+    import simvg_b200.ops as ops
+    assert T._ABSORB_MIN_KEYS <= 256
+    hc = copy.deepcopy(model_cfg("base", 512, 32, num_decoder_layers=6)["head"])
+    hc["in_channels"] = 96
+    hc.pop("type")
+    head = TextGuidedQuerySelectKDDETRHead(**copy.deepcopy(hc)).eval()
+    sd = synth_state_dict({k: v.float() for k, v in head.state_dict().items()}, seed=9)
+    head.load_state_dict(sd)
+    old = ops.linear
+    ops.linear = lambda x, W, b=None: torch.nn.functional.linear(x, W, b)   # CPU stand-in for the GEMM in THIS TEST ONLY
+    try:
+        B = 2
+        g = torch.Generator().manual_seed(4)
+        x_mm = torch.randn(B, 96, 16, 16, generator=g, requires_grad=True)
+        text, cls = torch.randn(B, 20, 96, generator=g), torch.randn(B, 96, generator=g)
+        batch = make_batch(B, 512, seed=6)
+        metas = batch["img_metas"]
+        for m in metas:
+            m["batch_input_shape"] = (512, 512)
+        losses, out = head.forward_train(x_mm, metas, cls_feat=cls, text_feat=text, gt_bbox=batch["gt_bbox"],
+                                         text_mask=batch["text_attention_mask"])
+        losses["loss_total"].backward()
+        g_ours = x_mm.grad.clone()
+    finally:
+        ops.linear = old
+    x2 = x_mm.detach().clone().requires_grad_(True)
+    ol, oo = O.head_forward_train({"head." + k: v for k, v in sd.items()}, hc, x2, copy.deepcopy(metas), cls, text,
+                                  batch["gt_bbox"], batch["text_attention_mask"])
+    ol["loss_total"].backward()
+    assert set(ol) <= set(losses)
+    for k in ol:
+        assert torch.allclose(losses[k], ol[k], rtol=5e-5, atol=1e-6), (k, float(losses[k]), float(ol[k]))
+    assert torch.allclose(out["outputs_coord_decoder_branch"], oo["outputs_coord_decoder_branch"], atol=2e-5)
+    assert out["outputs_coord_decoder_branch"].shape[0] == 6
+    rel_g = ((g_ours - x2.grad).norm() / x2.grad.norm()).item()
+    assert rel_g < 1e-4, rel_g
