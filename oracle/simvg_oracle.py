@@ -308,11 +308,15 @@ def detr_decoder(sd, prefix, num_layers, query, key, value, query_pos, key_pos, 
     return torch.stack(inter)
 
 
-def head_forward_general(sd, hc, x_mm, img_metas, cls_feat, text_feat, text_mask, prefix="head."):
-    """TextGuidedQuerySelectKDDETRHead.forward_general (tgqs_kd_detr_head.py:375-454), text_guided_query_generation=True."""
+def head_forward_general(sd, hc, x_mm, img_metas, cls_feat, text_feat, text_mask, prefix="head.", proj_hook=None):
+    """TextGuidedQuerySelectKDDETRHead.forward_general (tgqs_kd_detr_head.py:375-454), text_guided_query_generation=True.
+
+    proj_hook: optional callable applied to input_proj's output (oracle/bf16_emulation.py rounds its gradient there)."""
     nq = hc["num_queries"]
     B = x_mm.shape[0]
     x_mm = F.conv2d(x_mm, sd[prefix + "input_proj.weight"], sd[prefix + "input_proj.bias"])
+    if proj_hook is not None:
+        x_mm = proj_hook(x_mm)
     text_feat = _linear(sd, prefix + "input_text_proj", text_feat)
     cls_feat = _linear(sd, prefix + "input_cls_proj", cls_feat).unsqueeze(1)
     # x_mask_pos_enc (:322-338)
@@ -405,9 +409,10 @@ def _calc_loss(cls, coord, targets, world_size=1):
     return {k: v * _WEIGHTS[k.rsplit("_", 1)[0] if k[-1].isdigit() else k] for k, v in ld.items()}
 
 
-def head_forward_train(sd, hc, x_mm, img_metas, cls_feat, text_feat, gt_bbox, text_mask, prefix="head.", world_size=1):
+def head_forward_train(sd, hc, x_mm, img_metas, cls_feat, text_feat, gt_bbox, text_mask, prefix="head.", world_size=1,
+                       proj_hook=None):
     """forward_train (tgqs_kd_detr_head.py:456-572) for branch_loss_weight = {decoder[, balanced_distill]}."""
-    out = head_forward_general(sd, hc, x_mm, img_metas, cls_feat, text_feat, text_mask, prefix)
+    out = head_forward_general(sd, hc, x_mm, img_metas, cls_feat, text_feat, text_mask, prefix, proj_hook=proj_hook)
     blw = hc["branch_loss_weight"]
     tg = _gt_targets(gt_bbox, img_metas)
     tp = _teacher_targets(out["decoder_branch_output"], tg)

@@ -590,11 +590,7 @@ extern "C" int simvgb_attn_bwd(const simvgb_attn_args* a, void* stream) {
   SIMVGB_CUDA(cudaMemsetAsync(a->dq_acc_v, 0, sizeof(float) * (size_t)a->B * a->Lv * D, s));
   if (a->Lt > 0) SIMVGB_CUDA(cudaMemsetAsync(a->dq_acc_t, 0, sizeof(float) * (size_t)a->B * a->Lt * D, s));
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    SIMVGB_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
-    attr_set = true;
-  }
+  if (ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_kernel), kBwdSmem)) return -2;
   dim3 grid(p.g.ntiles, a->H, a->B);
   attn_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, s>>>(maps, p);
   SIMVGB_CUDA(cudaGetLastError());

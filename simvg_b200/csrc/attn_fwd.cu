@@ -356,11 +356,7 @@ extern "C" int simvgb_attn_fwd(const simvgb_attn_args* a, void* stream) {
   }
   CUtensorMap full, tail, text;
   if (make_attn_maps(&full, &tail, &text, p.g, a->qkv_v, a->qkv_t, 3 * D)) return -1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SIMVGB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
-    attr_set = true;
-  }
+  if (ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_kernel), kFwdSmem)) return -2;
   dim3 grid(p.g.ntiles, a->H, a->B);
   attn_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(full, tail, text, p);
   SIMVGB_CUDA(cudaGetLastError());

@@ -36,7 +36,9 @@ void set_error(const char* fmt, ...);
 // strides_bytes has rank-1 entries (stride of dim 1, dim 2). swizzle: 0 none, 1 = 128B.
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
-int sm_count();
+int sm_count();   // of the current device
+// Raises the dynamic shared-memory limit of kernel `func` once per (device, function).
+int ensure_dynamic_smem(const void* func, int bytes);
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

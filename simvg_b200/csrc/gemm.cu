@@ -362,12 +362,7 @@ static int launch_gemm(const simvgb_gemm_args* a, cudaStream_t stream) {
   p.rows_per_scale = a->rows_per_scale > 0 ? a->rows_per_scale : 1;
   p.accumulate = a->accumulate;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    SIMVGB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  if (ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_kernel<BN>), Cfg::kSmemBytes)) return -2;
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
   int grid = sm_count();
   if (grid > total) grid = total;

@@ -464,11 +464,7 @@ int launch_gemm_2cta(const simvgb_gemm_args* a, const simvgb_gemm_args* b, cudaS
   } else {
     tmA1 = tmA0; tmB1 = tmB0; p1 = p0;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    SIMVGB_CUDA(cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  if (ensure_dynamic_smem(reinterpret_cast<const void*>(gemm2_kernel), Gemm2Cfg::kSmemBytes)) return -2;
   const int total = p0.m_tiles * p0.n_tiles * p0.k_splits + tiles1;
   int clusters = sm_count() / 2;
   if (clusters > total) clusters = total;

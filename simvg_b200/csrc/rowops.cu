@@ -786,12 +786,8 @@ extern "C" int simvgb_ln_bwd(const simvgb_ln_bwd_args* a, void* stream) {
     const long long cap = (long long)sm_count() * 2;   // 255 registers x 128 threads: two resident blocks per SM
     if (blocks > cap) blocks = cap;
     const size_t ring_bytes = (size_t)kWideStages * 2 * p.C * 2 + kWideStages * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-      SIMVGB_CUDA(cudaFuncSetAttribute(ln_bwd_wide_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2 * 3072 * 2 + 64));
-      SIMVGB_CUDA(cudaFuncSetAttribute(ln_bwd_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2 * 4096 * 2 + 64));
-      attr_set = true;
-    }
+    if (ensure_dynamic_smem(reinterpret_cast<const void*>(ln_bwd_wide_kernel<3>), 3 * 2 * 3072 * 2 + 64)) return -2;
+    if (ensure_dynamic_smem(reinterpret_cast<const void*>(ln_bwd_wide_kernel<4>), 3 * 2 * 4096 * 2 + 64)) return -2;
     if (p.C == 3072) ln_bwd_wide_kernel<3><<<(unsigned)blocks, 128, ring_bytes, st>>>(p);
     else ln_bwd_wide_kernel<4><<<(unsigned)blocks, 128, ring_bytes, st>>>(p);
     SIMVGB_CUDA(cudaGetLastError());

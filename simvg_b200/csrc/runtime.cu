@@ -4,6 +4,8 @@
 #include <string.h>
 
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "simvg_b200.h"
@@ -70,15 +72,34 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
   return 0;
 }
 
+// Per-device caches (several devices may be driven from one process: nothing here is process-global state keyed on "first use").
+static const int kMaxDevices = 64;
+
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (device, function): remember which pairs were already raised.
+int ensure_dynamic_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<int, const void*>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& d : done)
+    if (d.first == dev && d.second == func) return 0;
+  SIMVGB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.emplace_back(dev, func);
+  return 0;
 }
 
 }  // namespace simvgb

@@ -1,0 +1,103 @@
+"""-m gpu: model-level parity at the BENCHMARKED geometries.
+
+  * ViT-B/16, 640x640 (L = 1621 tokens, 13 key tiles with a vision tail + text tile, ragged last M-tile in every GEMM), bs = 2,
+    6-layer decoder — BASELINE configs[1] at a batch the CPU oracle finishes in seconds;
+  * ViT-L/16 (D = 1024, H = 16, F = 4096): all 24 layers forward at 224x224, a 4-layer train step at 224x224 and a 2-layer
+    train step at the 768x768 geometry (Lv = 2305, L = 2325) of BASELINE configs[3].
+
+Every case is compared with TWO CPU oracles on identical weights and inputs:
+  fp32 oracle (oracle/simvg_oracle.py, pinned to the reference's own files)  -> losses / boxes within the north_star's 1e-3;
+        gradients within the bf16-operand rounding budget (the emulated oracle itself sits 1-8 % from the fp32 one:
+        see oracle/bf16_emulation.py), per tensor, relative L2 — no cosines, no "up to N may fail";
+  bf16-operand oracle (oracle/bf16_emulation.py: same algorithm, rounds where the kernels round) -> tight per-tensor
+        bounds: what is left is accumulation order + exp2/erf approximations, so a scale or bias-gradient bug cannot hide.
+The measured error distributions are also written to gpurun_out/parity_<case>.json.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from parity_utils import build_product, grad_errors, loss_errors, oracle_step, product_step, rel_l2, summarize
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _dump(name, rec):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_%s.json" % name), "w") as f:
+        json.dump(rec, f, indent=1, default=str)
+
+
+def _check_train_step(name, vit, S, P, B, dec_layers, enc_layers, lim):
+    from tools.synth import make_batch
+    cfg, model, sd = build_product(vit, S, P, seed=7, dec_layers=dec_layers, enc_layers=enc_layers)
+    gb, cb = make_batch(B, S, seed=21, device="cuda"), make_batch(B, S, seed=21, device="cpu")
+    losses, preds, grads = product_step(model, gb)
+    rec = {"case": name, "vit": vit, "S": S, "P": P, "B": B, "enc_layers": enc_layers or model.vis_enc.cfg["layers"]}
+    results = {}
+    for tag, emu in (("fp32", False), ("bf16emu", True)):
+        ol, op, og, _ = oracle_step(sd, cfg, vit, S, P, cb, emulate_bf16=emu, enc_layers=enc_layers)
+        le = loss_errors(losses, ol)
+        box = [(preds[i]["pred_bboxes"].cpu() - op[i]["pred_bboxes"]).abs().max().item() / S for i in range(2)
+               if op[i]["pred_bboxes"] is not None]
+        errs, skipped = grad_errors(grads, og)
+        results[tag] = (le, box, errs)
+        rec[tag] = {"loss_rel": le, "box_err_of_image": box, "grad": summarize(errs), "grad_skipped_zero": skipped}
+    _dump(name, rec)
+    for tag in ("fp32", "bf16emu"):
+        le, box, errs = results[tag]
+        assert max(le.values()) <= 1e-3, (tag, le)                       # north_star: outputs within 1e-3 relative
+        assert max(box) <= 1e-3, (tag, box)
+        assert len(errs) > 250
+        s = summarize(errs)
+        assert s["max"] <= lim[tag][0] and s["median"] <= lim[tag][1], (tag, s)
+    # unused parameters keep exactly-zero gradients
+    assert float(model.vis_enc.beit3.vision_embed.mask_token.grad.abs().sum()) == 0
+
+
+# (max, median) per-tensor relative-L2 gradient error allowed against each oracle
+_LIM_B = {"fp32": (0.12, 0.03), "bf16emu": (0.03, 0.006)}
+_LIM_L = {"fp32": (0.12, 0.03), "bf16emu": (0.03, 0.006)}
+
+
+def test_cfg2_geometry_train_step(lib):
+    """BASELINE configs[1] geometry: ViT-B/16, 640x640, 6-layer decoder, DWBD losses; bs = 2 (the oracle's affordable batch)."""
+    _check_train_step("cfg2_vitb16_640", "base", 640, 16, 2, 6, None, _LIM_B)
+
+
+def test_vit_large_224_train_step(lib):
+    """ViT-L/16 widths (D=1024, H=16, F=4096), first 4 encoder layers, 224x224, bs = 2: full train step."""
+    _check_train_step("vitl16_224_4layers", "large", 224, 16, 2, 3, 4, _LIM_L)
+
+
+def test_vit_large_768_geometry_train_step(lib):
+    """ViT-L/16 at the 768x768 geometry of BASELINE configs[3] (Lv = 2305, L = 2325: 19 key tiles), 2 encoder layers, bs = 1."""
+    _check_train_step("vitl16_768_2layers", "large", 768, 16, 1, 3, 2, _LIM_L)
+
+
+def test_vit_large_24_layers_forward(lib):
+    """All 24 ViT-L layers, forward only (features + losses + boxes) at 224x224."""
+    from tools.synth import make_batch
+    vit, S, P, B = "large", 224, 16, 2
+    cfg, model, sd = build_product(vit, S, P, seed=9)
+    gb, cb = make_batch(B, S, seed=22, device="cuda"), make_batch(B, S, seed=22, device="cpu")
+    losses, preds, _ = product_step(model, gb, backward=False)
+    with torch.no_grad():
+        feats = model.vis_enc(gb["img"], gb["ref_expr_inds"], gb["text_attention_mask"])
+    rec = {"case": "vitl16_224_24layers_fwd"}
+    for tag, emu, flim in (("fp32", False, 2e-2), ("bf16emu", True, 4e-3)):
+        ol, op, _, om = oracle_step(sd, cfg, vit, S, P, cb, emulate_bf16=emu, backward=False)
+        with torch.no_grad():
+            ofe = om._features(cb["img"], cb["ref_expr_inds"], cb["text_attention_mask"])
+        fe = {"img": rel_l2(feats[0].transpose(1, 2).reshape(ofe[0].shape), ofe[0]), "text": rel_l2(feats[1], ofe[1]),
+              "cls": rel_l2(feats[2], ofe[2])}
+        le = loss_errors(losses, ol)
+        box = [(preds[i]["pred_bboxes"].cpu() - op[i]["pred_bboxes"]).abs().max().item() / S for i in range(2)]
+        rec[tag] = {"feat_rel_l2": fe, "loss_rel": le, "box_err_of_image": box}
+        _dump("vitl16_224_24layers_fwd", rec)
+        assert max(le.values()) <= 1e-3 and max(box) <= 1e-3, (tag, le, box)
+        assert max(fe.values()) <= flim, (tag, fe)
