@@ -54,7 +54,7 @@ class _AttnCore(torch.autograd.Function):
 
     forward : e = exp(S - rowmax) in fp32, O = (bf16(e) @ V) / sum(e), O stored bf16.
     backward: P = e / sum(e) recomputed in fp32; dV = bf16(P)^T dO; dP = dO V^T; delta = rowsum(dO * O);
-              dS = bf16(P * (dP - delta)); dQ = dS K; dK = dS^T Q.   (torchscale MultiheadAttention)"""
+              dS = bf16(bf16(P) * (dP - delta)); dQ = dS K; dK = dS^T Q.   (torchscale MultiheadAttention)"""
 
     @staticmethod
     def forward(ctx, q, k, v, kpm):
@@ -74,7 +74,7 @@ class _AttnCore(torch.autograd.Function):
         dv = _r(p).transpose(-1, -2) @ do
         dp = do @ v.transpose(-1, -2)
         delta = (do * o).sum(-1, keepdim=True)
-        ds = _r(p * (dp - delta))
+        ds = _r(_r(p) * (dp - delta))   # the kernel keeps only the packed bf16 P^T live across the dP^T wait
         return ds @ k, ds.transpose(-1, -2) @ q, dv, None
 
 

@@ -5,40 +5,39 @@
 // ever materialising the [B*H, L, L] score tensor.  q arrives pre-scaled by head_dim^-0.5 (fused into the QKV GEMM
 // epilogue, matching `q *= self.scaling` after the bias add).
 //
-// One CTA = one 128-query tile of one (b, h); two CTAs are co-resident per SM so one CTA's softmax overlaps the other's
-// MMAs.  Warp roles:  0 = TMA producer, 1 = tcgen05.mma issuer, 2-9 = softmax: two warps per TMEM lane quarter, each
-// thread owns one query row x 64 key columns (row max exchanged through smem) so every SM sub-partition always has
-// several softmax warps to switch between while MUFU / TMEM loads are in flight.
-//   S = Q K_j^T   : tcgen05.mma M=128 N=128 K=64, both operands K-major, S in TMEM columns [0,128)
-//   O += P V_j    : P (bf16 pairs packed in 32-bit TMEM columns [192,256)) is written by the softmax threads with
-//                   tcgen05.st and consumed as the A operand straight from TMEM (shared memory only feeds B: at
-//                   head_dim 64 the kernel is bound by shared-memory bandwidth, and P through smem cost 64 KB of the
-//                   144 KB moved per tile); V_j read MN-major straight from its token-major TMA tile; O in TMEM
-//                   columns [128,192)
-// Online softmax with lazy rescaling (O is only rescaled when a row max grows by more than 2^8).
+// Round-2 design (round 1 ran one 128-query tile per CTA, two CTAs per SM, and sat at 0.3 of the tensor peak because every
+// CTA serialised S -> softmax -> P -> PV and the two halves of a row exchanged their maxima through shared memory):
+//   * persistent, one CTA per SM, each work item = TWO 128-query tiles (A, B) of one (sample, head) that share every K/V
+//     tile: the tensor pipe works on one tile while the MUFU/FMA pipes run the other tile's softmax (ping-pong), and K/V
+//     cross L2 -> smem once per 256 queries instead of once per 128;
+//   * one softmax thread owns one whole query row of a key tile (128 scores in registers, `setmaxnreg` moves registers from
+//     the two single-lane control warps to the softmax warpgroups): row max / row sum need no shuffle, no smem, no barrier;
+//   * S_X(j+1) is issued as soon as the softmax has pulled S_X(j) out of TMEM (P has its own TMEM columns), so scores are
+//     always waiting when a softmax warpgroup comes back; the next work item's Q / K / V loads and first S products overlap
+//     this item's epilogue;
+//   * P goes to TMEM as packed bf16 pairs (tcgen05.st) and is the A operand of O += P V (TS-form MMA); V is consumed
+//     MN-major straight from its token-major TMA tile; online softmax with lazy rescaling (O is touched only when a row
+//     maximum grows by more than 2^8).
+// Warp roles: 0 = TMA producer, 1 = tcgen05.mma issuer, 2-3 = idle (register donors), 4-7 = softmax of tile A, 8-11 = softmax
+// of tile B.  TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)  P_A [384,448)  P_B [448,512).
 #include <stdlib.h>
 
 #include "attn_common.cuh"
-
-#ifdef SIMVGB_ATTN_ABLATE   // timing ablations (tools/attn_ablate.py): build with -DSIMVGB_ATTN_ABLATE
-#define SIMVGB_DBG(p) ((p).dbg)
-#else
-#define SIMVGB_DBG(p) 0
-#endif
 #include "simvg_b200.h"
 
 namespace simvgb {
 
-static long long* g_fwd_trace = nullptr;
-
 #ifndef SIMVGB_FWD_POLY
-#define SIMVGB_FWD_POLY 0   // exponentials per group of 4 evaluated on the FMA pipe instead of MUFU (0, 1 or 2)
+#define SIMVGB_FWD_POLY 0   // of every 8 exponentials, this many are evaluated on the FMA pipe instead of MUFU (full tiles only)
 #endif
-constexpr int kFwdThreads = 320;
-constexpr int kSoftmaxThreads = 256;
-constexpr int kSlots = 4;  // staging tiles: K double-buffered (slots 0,1), V double-buffered (slots 2,3); both prefetched a tile ahead
-constexpr int kFwdSmem = kTileBytes /*Q*/ + kSlots * kTileBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*row-max exchange*/;
+#ifndef SIMVGB_FWD_KS
+#define SIMVGB_FWD_KS 3
+#endif
+constexpr int kFwdThreads = 384;
+constexpr int kKS = SIMVGB_FWD_KS;   // K ring depth = V ring depth
+constexpr int kFwdSmem = (2 + 2 * kKS) * kTileBytes + 1024 /*align*/ + 512 /*barriers*/;
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kRegsCtl = 88, kRegsSoftmax = 208;   // (88 + 2 * 208) * 128 threads = 64,512 registers = 168 * 384
 
 struct AttnFwdParams {
   AttnGeom g;
@@ -46,60 +45,94 @@ struct AttnFwdParams {
   bf16* out_v;               // [B*Lv, D]
   bf16* out_t;               // [B*Lt, D]
   float* lse;                // [B, H, ntiles*128]  log2-domain logsumexp of each query row
-  int dbg;                   // timing ablations (SIMVGB_ATTN_DEBUG, tools/attn_ablate.py); 0 in production
-  long long* ts;             // optional clock64 trace of CTA (0,0,0) (tools/attn_trace.py)
+  int npairs;                // ntiles / 2  (work items with two query tiles)
+  int n_full_items;          // B * H * npairs
+  int n_items;               // + B * H single-tile items when ntiles is odd
 };
 
-__device__ __forceinline__ void pair_sync(int quarter) {   // the two softmax warps that share a TMEM lane quarter
-  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+struct FwdItem {
+  int b, h, tA, tB;   // tB < 0: only tile A
+};
+
+__device__ __forceinline__ FwdItem decode_item(const AttnFwdParams& p, int it) {
+  FwdItem w;
+  if (it < p.n_full_items) {
+    const int bh = it / p.npairs, qp = it - bh * p.npairs;
+    w.b = bh / p.g.H; w.h = bh - w.b * p.g.H; w.tA = 2 * qp; w.tB = 2 * qp + 1;
+  } else {
+    const int bh = it - p.n_full_items;
+    w.b = bh / p.g.H; w.h = bh - w.b * p.g.H; w.tA = p.g.ntiles - 1; w.tB = -1;
+  }
+  return w;
 }
 
-__global__ void __launch_bounds__(kFwdThreads, 2)
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// exp2 of 32 scores (already in registers) -> 16 packed bf16 pairs, returns their fp32 sum.  x = s * log2e - m.
+template <bool kPoly>
+__device__ __forceinline__ float exp_chunk(const uint32_t (&s)[32], uint32_t (&pk)[16], float neg_m) {
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float x0 = fmaf(__uint_as_float(s[2 * i]), kLog2e, neg_m);
+    const float x1 = fmaf(__uint_as_float(s[2 * i + 1]), kLog2e, neg_m);
+    float e0, e1;
+    // exponent i of this chunk goes to the FMA pipe when (2i mod 8) < SIMVGB_FWD_POLY (resp. 2i+1)
+    if (kPoly && ((2 * i) & 7) < SIMVGB_FWD_POLY) e0 = ex2_fma(fmaxf(x0, -100.f)); else e0 = ex2_approx(x0);
+    if (kPoly && ((2 * i + 1) & 7) < SIMVGB_FWD_POLY) e1 = ex2_fma(fmaxf(x1, -100.f)); else e1 = ex2_approx(x1);
+    sum0 += e0;
+    sum1 += e1;
+    pk[i] = pack_bf16x2(e0, e1);   // TMEM column c of P holds keys 2c (low half), 2c+1 (high half)
+  }
+  return sum0 + sum1;
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_constant__ CUtensorMap map_tail,
                 const __grid_constant__ CUtensorMap map_text, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sKV = smem + kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + kSlots) * kTileBytes);
-  uint64_t* q_full = bars;
-  uint64_t* slot_full = bars + 1;             // [kSlots]  0,1 = K ring, 2,3 = V ring
-  uint64_t* slot_empty = bars + 1 + kSlots;   // [kSlots]
-  uint64_t* s_full = bars + 1 + 2 * kSlots;
-  uint64_t* s_empty = s_full + 1;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* pv_done = s_full + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
-  uint32_t* masks = tmem_slot + 2;            // [2][4] validity bits of the (at most two) partial tiles
-  float* xchg = reinterpret_cast<float*>(smem + (1 + kSlots) * kTileBytes + 256);  // [2 parity][2 halves][128 rows]
+  uint8_t* sQ = smem;                              // [2]
+  uint8_t* sK = smem + 2 * kTileBytes;             // [kKS]
+  uint8_t* sV = smem + (2 + kKS) * kTileBytes;     // [kKS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + 2 * kKS) * kTileBytes);
+  uint64_t* q_full = bars;                 // [2]
+  uint64_t* q_empty = bars + 2;            // [2]
+  uint64_t* k_full = bars + 4;             // [kKS]
+  uint64_t* k_empty = k_full + kKS;        // [kKS]
+  uint64_t* v_full = k_empty + kKS;        // [kKS]
+  uint64_t* v_empty = v_full + kKS;        // [kKS]
+  uint64_t* s_full = v_empty + kKS;        // [2]  S_X(j) complete
+  uint64_t* s_free = s_full + 2;           // [2]  softmax X holds S_X(j) in registers
+  uint64_t* p_full = s_full + 4;           // [2]  P_X(j) written (and O_X rescaled if it had to be)
+  uint64_t* pv_done = s_full + 6;          // [2]  O_X += P_X(j) V(j) complete
+  uint64_t* o_free = s_full + 8;           // [2]  epilogue X holds O_X in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 10);
 
   const AttnGeom& g = p.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int nk = g.ntiles;
 
   // Zero the staging tiles: partial (tail/text) tiles only overwrite some rows, the rest must stay finite.
   {
     uint4* z = reinterpret_cast<uint4*>(smem);
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < (1 + kSlots) * kTileBytes / 16; i += kFwdThreads) z[i] = zero;
+    for (int i = threadIdx.x; i < (2 + 2 * kKS) * kTileBytes / 16; i += kFwdThreads) z[i] = zero;
   }
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < kSlots; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, kSoftmaxThreads / 32);   // one elected arrival per softmax warp
-    mbar_init(p_full, kSoftmaxThreads / 32);
-    mbar_init(pv_done, 1);
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&q_full[x], 1); mbar_init(&q_empty[x], 1);
+      mbar_init(&s_full[x], 1); mbar_init(&s_free[x], 4);     // one elected arrival per softmax warp
+      mbar_init(&p_full[x], 4); mbar_init(&pv_done[x], 1); mbar_init(&o_free[x], 4);
+    }
+    for (int s = 0; s < kKS; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
     fence_barrier_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {   // warps 2-5: first partial tile, warps 6-9: second partial tile
-    const int which = (threadIdx.x - 64) >> 7;
-    const int t = g.nfull + which;
-    if (t < nk) build_tile_mask(masks + 4 * which, g, p.pad, b, t, (threadIdx.x - 64) & 127);
-  }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   fence_proxy_async();  // generic-proxy zero fill -> visible before TMA (async proxy) writes
@@ -107,209 +140,255 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (uniform registers for UTCHMMA)
-  const uint32_t tmS = tmem, tmO = tmem + 128, tmP = tmem + 192;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      const int colq = h * kHeadDim, colk = g.D + h * kHeadDim, colv = 2 * g.D + h * kHeadDim;
-      load_virtual_tile(sQ, q_full, g, &map_full, &map_tail, &map_text, qt, colq, b);
-      auto load_k = [&](int j) {
-        const int slot = j & 1;
-        mbar_wait(&slot_empty[slot], ((j >> 1) & 1) ^ 1);       // freed when S_{j-2} retired
-        load_virtual_tile(sKV + slot * kTileBytes, &slot_full[slot], g, &map_full, &map_tail, &map_text, j, colk, b);
-      };
-      auto load_v = [&](int j) {
-        const int slot = 2 + (j & 1);
-        mbar_wait(&slot_empty[slot], ((j >> 1) & 1) ^ 1);       // freed when P V_{j-2} retired
-        load_virtual_tile(sKV + slot * kTileBytes, &slot_full[slot], g, &map_full, &map_tail, &map_text, j, colv, b);
-      };
-      load_k(0);
-      for (int j = 0; j < nk; ++j) {
-        if (j + 1 < nk) load_k(j + 1);
-        load_v(j);
+  if (warp < 4) {
+    reg_dec<kRegsCtl>();
+    if (warp == 0) {
+      // ------------------------------ TMA producer ------------------------------
+      if (lane == 0) {
+        uint32_t kc = 0, vc = 0, qc[2] = {0, 0};
+        for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+          const FwdItem w = decode_item(p, it);
+          const int colq = w.h * kHeadDim, colk = g.D + colq, colv = 2 * g.D + colq;
+          auto load_q = [&](int x, int t) {
+            mbar_wait(&q_empty[x], (qc[x] & 1) ^ 1);          // freed when the previous item's last S_X retired
+            load_virtual_tile(sQ + x * kTileBytes, &q_full[x], g, &map_full, &map_tail, &map_text, t, colq, w.b);
+            ++qc[x];
+          };
+          auto load_k = [&](int j) {
+            const uint32_t slot = kc % kKS;
+            mbar_wait(&k_empty[slot], ((kc / kKS) & 1) ^ 1);
+            load_virtual_tile(sK + slot * kTileBytes, &k_full[slot], g, &map_full, &map_tail, &map_text, j, colk, w.b);
+            ++kc;
+          };
+          auto load_v = [&](int j) {
+            const uint32_t slot = vc % kKS;
+            mbar_wait(&v_empty[slot], ((vc / kKS) & 1) ^ 1);
+            load_virtual_tile(sV + slot * kTileBytes, &v_full[slot], g, &map_full, &map_tail, &map_text, j, colv, w.b);
+            ++vc;
+          };
+          load_q(0, w.tA);
+          load_k(0);
+          if (w.tB >= 0) load_q(1, w.tB);
+          load_v(0);
+          for (int j = 1; j < nk; ++j) { load_k(j); load_v(j); }
+        }
       }
-    }
-  } else if (warp == 1) {
-    // MMA issuer: warp-uniform control flow, single-lane issue (keeps descriptors in uniform registers).
-    const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-    const uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);  // A = P (K-major), B = V (MN-major)
-    const uint64_t dQ = umma_smem_desc(smem_u32(sQ), 16, 1024);
-    const uint64_t dKV_k = umma_smem_desc(smem_u32(sKV), 16, 1024), dKV_mn = umma_smem_desc(smem_u32(sKV), 8192, 1024);
-    auto issue_s = [&](int j) {
-      const int slot = j & 1;
-      mbar_wait(&slot_full[slot], (j >> 1) & 1);
-      tc_fence_after();
-      const uint64_t dk = dKV_k + slot * (kTileBytes >> 4);
-      if (elect_one()) {
+    } else if (warp == 1) {
+      // ------------------------------ MMA issuer: warp-uniform control flow, single-lane issue ------------------------------
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);  // A = P (TMEM), B = V (MN-major)
+      const uint64_t dQ0 = umma_smem_desc(smem_u32(sQ), 16, 1024);
+      const uint64_t dK0 = umma_smem_desc(smem_u32(sK), 16, 1024);
+      const uint64_t dV0 = umma_smem_desc(smem_u32(sV), 8192, 1024);
+      constexpr uint32_t kStep = kTileBytes >> 4;
+      uint32_t kc = 0, vc = 0, sc[2] = {0, 0}, pc[2] = {0, 0}, ic[2] = {0, 0};
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        const FwdItem w = decode_item(p, it);
+        const bool both = w.tB >= 0;
+        // S_X = Q_X K_j^T into TMEM columns [128 X, 128 X + 128); `last` also releases the Q_X buffer
+        auto issue_s = [&](int x, uint32_t kslot, bool last) {
+          mbar_wait(&s_free[x], (sc[x] & 1) ^ 1);             // softmax X has pulled the previous S_X out of TMEM
+          tc_fence_after();
+          const uint64_t dq = dQ0 + x * kStep, dk = dK0 + kslot * kStep;
+          if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kHeadDim / 16; ++k) umma_f16_ss(tmS, dQ + 2 * k, dk + 2 * k, idesc_s, k > 0);
-        umma_commit(&slot_empty[slot]);
-        umma_commit(s_full);
-      }
-      __syncwarp();
-    };
-    const bool trace = p.ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
-    mbar_wait(q_full, 0);
-    issue_s(0);
-    for (int j = 0; j < nk; ++j) {
-      if (trace) p.ts[j * 8 + 0] = clock64();
-      mbar_wait(s_empty, j & 1);  // softmax has consumed S_j
-      if (trace) p.ts[j * 8 + 1] = clock64();
-      if (j + 1 < nk) issue_s(j + 1);
-      if (trace) p.ts[j * 8 + 2] = clock64();
-      const int slot = 2 + (j & 1);
-      mbar_wait(p_full, j & 1);
-      if (trace) p.ts[j * 8 + 3] = clock64();
-      mbar_wait(&slot_full[slot], (j >> 1) & 1);
-      if (trace) p.ts[j * 8 + 4] = clock64();
-      tc_fence_after();
-      const uint64_t dv = dKV_mn + slot * (kTileBytes >> 4);
-      if (elect_one()) {
-        if (!(SIMVGB_DBG(p) & 8))
+            for (int k = 0; k < kHeadDim / 16; ++k) umma_f16_ss(tmem + 128 * x, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+            umma_commit(&s_full[x]);
+            if (last) umma_commit(&q_empty[x]);
+          }
+          __syncwarp();
+          ++sc[x];
+        };
+        // O_X (+)= P_X V_j
+        auto issue_pv = [&](int x, uint32_t vslot, bool first) {
+          mbar_wait(&p_full[x], pc[x] & 1);
+          if (first) mbar_wait(&o_free[x], (ic[x] & 1) ^ 1);  // the previous item's epilogue has read O_X
+          tc_fence_after();
+          const uint64_t dv = dV0 + vslot * kStep;
+          if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k)   // A = P[:, 16k .. 16k+16) = 8 packed TMEM columns
-          umma_f16_ts(tmO, tmP + 8 * k, dv + k * 128, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&slot_empty[slot]);
-        umma_commit(pv_done);
+            for (int k = 0; k < kTile / 16; ++k)   // A = P[:, 16k .. 16k+16) = 8 packed TMEM columns
+              umma_f16_ts(tmem + 256 + 64 * x, tmem + 384 + 64 * x + 8 * k, dv + k * 128, idesc_o, (!first || k > 0) ? 1u : 0u);
+            umma_commit(&pv_done[x]);
+          }
+          __syncwarp();
+          ++pc[x];
+        };
+        uint32_t kslot = kc % kKS;
+        mbar_wait(&q_full[0], ic[0] & 1);
+        mbar_wait(&k_full[kslot], (kc / kKS) & 1);
+        issue_s(0, kslot, nk == 1);
+        if (both) {
+          mbar_wait(&q_full[1], ic[1] & 1);
+          issue_s(1, kslot, nk == 1);
+        }
+        if (elect_one()) umma_commit(&k_empty[kslot]);
+        __syncwarp();
+        ++kc;
+        for (int j = 0; j < nk; ++j) {
+          const bool more = j + 1 < nk;
+          const uint32_t vslot = vc % kKS;
+          kslot = kc % kKS;
+          if (more) {
+            mbar_wait(&k_full[kslot], (kc / kKS) & 1);
+            issue_s(0, kslot, j + 2 == nk);
+          }
+          mbar_wait(&v_full[vslot], (vc / kKS) & 1);
+          issue_pv(0, vslot, j == 0);
+          if (both) {
+            if (more) issue_s(1, kslot, j + 2 == nk);
+            issue_pv(1, vslot, j == 0);
+          }
+          if (elect_one()) {
+            if (more) umma_commit(&k_empty[kslot]);
+            umma_commit(&v_empty[vslot]);
+          }
+          __syncwarp();
+          if (more) ++kc;
+          ++vc;
+        }
+        ++ic[0];
+        if (both) ++ic[1];
       }
-      __syncwarp();
-      if (trace) p.ts[j * 8 + 5] = clock64();
     }
   } else {
-    // ------------------------------ softmax: thread = (query row, 64-column half) ------------------------------
+    reg_inc<kRegsSoftmax>();
+    // ------------------------------ softmax + epilogue: thread = one query row of tile X ------------------------------
+    const int x = (warp - 4) >> 2;
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-    const uint32_t col_base = half * 64;
-    float m = -INFINITY, l = 0.f;   // l: partial row sum over this thread's columns
-    for (int j = 0; j < nk; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      const bool partial = j >= g.nfull;
-      const uint32_t* mk = masks + 4 * (j - g.nfull) + half * 2;
-      uint32_t va[32], vb[32];
-      if (!(SIMVGB_DBG(p) & 1)) {
-        tmem_ld32(tmS + lane_base + col_base, va);
-        tmem_ld32(tmS + lane_base + col_base + 32, vb);
-        tmem_wait_ld();
-      } else {
+    const uint32_t tmS = tmem + 128 * x + lane_base, tmO = tmem + 256 + 64 * x + lane_base, tmP = tmem + 384 + 64 * x + lane_base;
+    uint32_t sc = 0, pc = 0;
+    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+      const FwdItem w = decode_item(p, it);
+      const int qt = x == 0 ? w.tA : w.tB;
+      if (qt < 0) continue;
+      // validity bits of the (at most two) partial key tiles of sample b: bit c of word [t][k] = key t*128 + 32k + c is a real,
+      // unpadded token.  Every lane tests 8 positions; one ballot per word (warp-uniform result).
+      uint32_t mk[2][4];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { va[i] = 0; vb[i] = 0; }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);   // scores are in registers: the MMA warp may overwrite S with Q K_{j+1}^T
-      if (partial) {
-        const uint32_t ba = mk[0], bb = mk[1];
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int v = (g.nfull + t) * kTile + 32 * k + lane;
+          bool ok = v < g.Lv;
+          if (!ok && v >= g.T0 && v < g.T0 + g.Lt) ok = (p.pad == nullptr) || (p.pad[w.b * g.Lt + (v - g.T0)] == 0);
+          mk[t][k] = __ballot_sync(0xffffffffu, ok);
+        }
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < nk; ++j) {
+        mbar_wait(&s_full[x], sc & 1);
+        ++sc;
+        tc_fence_after();
+        uint32_t s0[32], s1[32], s2[32], s3[32];
+        tmem_ld32(tmS, s0);
+        tmem_ld32(tmS + 32, s1);
+        tmem_ld32(tmS + 64, s2);
+        tmem_ld32(tmS + 96, s3);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[x]);   // scores are in registers: the MMA warp may overwrite S_X
+        const bool partial = j >= g.nfull;
+        if (partial) {
+          const int t = j - g.nfull;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (!((mk[t][0] >> i) & 1u)) s0[i] = 0xff800000u;   // -inf
+            if (!((mk[t][1] >> i) & 1u)) s1[i] = 0xff800000u;
+            if (!((mk[t][2] >> i) & 1u)) s2[i] = 0xff800000u;
+            if (!((mk[t][3] >> i) & 1u)) s3[i] = 0xff800000u;
+          }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          if (!((ba >> i) & 1u)) va[i] = 0xff800000u;   // -inf
-          if (!((bb >> i) & 1u)) vb[i] = 0xff800000u;
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s2[i]), __uint_as_float(s3[i])));
         }
-      }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
-      float* xm = xchg + (j & 1) * 256;
-      if (!(SIMVGB_DBG(p) & 16)) {
-        xm[half * 128 + r] = mx;
-        pair_sync(quarter);
-        mx = fmaxf(mx, xm[(half ^ 1) * 128 + r]);
-      }
-      mx *= kLog2e;
-      const bool need = mx > m + 8.0f;       // lazy rescale threshold (log2 units); true on the first tile
-      const float m_use = need ? mx : m;
-      const float alpha = need ? ex2_approx(m - m_use) : 1.0f;
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);     // P buffer free, O up to tile j-1 complete
-        if (__any_sync(0xffffffffu, need)) {
+        const float mx = fmaxf(mx0, mx1) * kLog2e;
+        const bool need = mx > m + 8.0f;       // lazy rescale threshold (log2 units); true on the first tile
+        const float m_use = need ? mx : m;
+        const float alpha = need ? ex2_approx(m - m_use) : 1.0f;
+        mbar_wait(&pv_done[x], (pc & 1) ^ 1);  // P_X buffer free, O_X complete up to tile j-1
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
           tc_fence_after();
-          uint32_t v[32];
-          tmem_ld32(tmO + lane_base + half * 32, v);
-          tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st32(tmO + lane_base + half * 32, v);
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmO + 32 * c, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(tmO + 32 * c, v);
+          }
           tmem_wait_st();
         }
-      }
-      // exp2 and bf16 packing fused (in place: pair i of va/vb lands in word i), so no fp32 probability outlives its pair
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float a0, a1, b0, b1;
-        if (SIMVGB_DBG(p) & 2) {
-          a0 = __uint_as_float(va[2 * i]); a1 = __uint_as_float(va[2 * i + 1]);
-          b0 = __uint_as_float(vb[2 * i]); b1 = __uint_as_float(vb[2 * i + 1]);
+        const float neg_m = -m_use;
+        float sum = 0.f;
+        uint32_t pk[16];
+        if (partial) {   // masked scores are -inf: MUFU handles them, the FMA-pipe exp2 does not
+          sum += exp_chunk<false>(s0, pk, neg_m); tmem_st16(tmP, pk);
+          sum += exp_chunk<false>(s1, pk, neg_m); tmem_st16(tmP + 16, pk);
+          sum += exp_chunk<false>(s2, pk, neg_m); tmem_st16(tmP + 32, pk);
+          sum += exp_chunk<false>(s3, pk, neg_m); tmem_st16(tmP + 48, pk);
         } else {
-          a0 = ex2_approx(fmaf(__uint_as_float(va[2 * i]), kLog2e, -m_use));
-          a1 = ex2_approx(fmaf(__uint_as_float(va[2 * i + 1]), kLog2e, -m_use));
-#if SIMVGB_FWD_POLY >= 2
-          const float xb0 = fmaf(__uint_as_float(vb[2 * i]), kLog2e, -m_use);
-          b0 = partial ? ex2_approx(xb0) : ex2_fma(fmaxf(xb0, -100.f));
-#else
-          b0 = ex2_approx(fmaf(__uint_as_float(vb[2 * i]), kLog2e, -m_use));
-#endif
-#if SIMVGB_FWD_POLY >= 1
-          // full tiles only (warp-uniform): masked scores are -inf, which the FMA-pipe exp2 does not handle
-          const float xb1 = fmaf(__uint_as_float(vb[2 * i + 1]), kLog2e, -m_use);
-          b1 = partial ? ex2_approx(xb1) : ex2_fma(fmaxf(xb1, -100.f));
-#else
-          b1 = ex2_approx(fmaf(__uint_as_float(vb[2 * i + 1]), kLog2e, -m_use));
-#endif
+          sum += exp_chunk<(SIMVGB_FWD_POLY > 0)>(s0, pk, neg_m); tmem_st16(tmP, pk);
+          sum += exp_chunk<(SIMVGB_FWD_POLY > 0)>(s1, pk, neg_m); tmem_st16(tmP + 16, pk);
+          sum += exp_chunk<(SIMVGB_FWD_POLY > 0)>(s2, pk, neg_m); tmem_st16(tmP + 32, pk);
+          sum += exp_chunk<(SIMVGB_FWD_POLY > 0)>(s3, pk, neg_m); tmem_st16(tmP + 48, pk);
         }
-        sum += (a0 + a1) + (b0 + b1);
-        va[i] = pack_bf16x2(a0, a1);   // TMEM column c of P holds keys 2c (low half), 2c+1 (high half)
-        vb[i] = pack_bf16x2(b0, b1);
-      }
-      if (!(SIMVGB_DBG(p) & 4)) {
-        tmem_st16x2(tmP + lane_base + half * 32, va, vb);
         tmem_wait_st();
+        l = l * alpha + sum;
+        m = m_use;
+        tc_fence_before();     // P (and a rescaled O) are in TMEM: order them before the MMA warp's tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[x]);
+        ++pc;
       }
-      l = l * alpha + sum;
-      m = m_use;
-      tc_fence_before();     // P is in TMEM (tcgen05.st completed above): order it before the MMA warp's tcgen05.mma
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-    // ------------------------------ epilogue ------------------------------
-    float* xs = xchg + (nk & 1) * 256;
-    xs[half * 128 + r] = l;
-    pair_sync(quarter);
-    l += xs[(half ^ 1) * 128 + r];
-    mbar_wait(pv_done, (nk - 1) & 1);
-    tc_fence_after();
-    const int qv = qt * kTile + r;
-    bf16* dst = nullptr;
-    if (qv < g.Lv) dst = p.out_v + ((long long)b * g.Lv + qv) * g.D + h * kHeadDim;
-    else if (qv >= g.T0 && qv < g.T0 + g.Lt) dst = p.out_t + ((long long)b * g.Lt + (qv - g.T0)) * g.D + h * kHeadDim;
-    const float inv = 1.0f / l;
-    {
-      uint32_t v[32];
-      tmem_ld32(tmO + lane_base + half * 32, v);
+      // ------------------------------ epilogue ------------------------------
+      mbar_wait(&pv_done[x], (pc - 1) & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tmO, o0);
+      tmem_ld32(tmO + 32, o1);
       tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[x]);    // the next item's first P V may overwrite O_X
+      const int qv = qt * kTile + r;
+      bf16* dst = nullptr;
+      if (qv < g.Lv) dst = p.out_v + ((long long)w.b * g.Lv + qv) * g.D + w.h * kHeadDim;
+      else if (qv >= g.T0 && qv < g.T0 + g.Lt) dst = p.out_t + ((long long)w.b * g.Lt + (qv - g.T0)) * g.D + w.h * kHeadDim;
+      const float inv = 1.0f / l;
       if (dst != nullptr) {
-        uint4* o = reinterpret_cast<uint4*>(dst + half * 32);
+        uint4* o = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          o[q4] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * q4]) * inv, __uint_as_float(v[8 * q4 + 1]) * inv),
-                             pack_bf16x2(__uint_as_float(v[8 * q4 + 2]) * inv, __uint_as_float(v[8 * q4 + 3]) * inv),
-                             pack_bf16x2(__uint_as_float(v[8 * q4 + 4]) * inv, __uint_as_float(v[8 * q4 + 5]) * inv),
-                             pack_bf16x2(__uint_as_float(v[8 * q4 + 6]) * inv, __uint_as_float(v[8 * q4 + 7]) * inv));
+        for (int q4 = 0; q4 < 4; ++q4) {
+          o[q4] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * q4]) * inv, __uint_as_float(o0[8 * q4 + 1]) * inv),
+                             pack_bf16x2(__uint_as_float(o0[8 * q4 + 2]) * inv, __uint_as_float(o0[8 * q4 + 3]) * inv),
+                             pack_bf16x2(__uint_as_float(o0[8 * q4 + 4]) * inv, __uint_as_float(o0[8 * q4 + 5]) * inv),
+                             pack_bf16x2(__uint_as_float(o0[8 * q4 + 6]) * inv, __uint_as_float(o0[8 * q4 + 7]) * inv));
+          o[4 + q4] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * q4]) * inv, __uint_as_float(o1[8 * q4 + 1]) * inv),
+                                 pack_bf16x2(__uint_as_float(o1[8 * q4 + 2]) * inv, __uint_as_float(o1[8 * q4 + 3]) * inv),
+                                 pack_bf16x2(__uint_as_float(o1[8 * q4 + 4]) * inv, __uint_as_float(o1[8 * q4 + 5]) * inv),
+                                 pack_bf16x2(__uint_as_float(o1[8 * q4 + 6]) * inv, __uint_as_float(o1[8 * q4 + 7]) * inv));
+        }
       }
+      // positions of the virtual axis that are not tokens get LSE = +inf: the backward then computes P = exp2(S - inf) = 0
+      // for them without any query-side masking
+      if (p.lse != nullptr)
+        p.lse[((long long)w.b * g.H + w.h) * (g.ntiles * kTile) + qv] = dst != nullptr ? m + log2f(l) : INFINITY;
     }
-    // positions of the virtual axis that are not tokens get LSE = +inf: the backward then computes P = exp2(S - inf) = 0
-    // for them without any query-side masking
-    if (p.lse != nullptr && half == 0)
-      p.lse[((long long)b * g.H + h) * (g.ntiles * kTile) + qv] = dst != nullptr ? m + log2f(l) : INFINITY;
-    tc_fence_before();
   }
 
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -349,15 +428,14 @@ extern "C" int simvgb_attn_fwd(const simvgb_attn_args* a, void* stream) {
   p.out_v = reinterpret_cast<bf16*>(a->out_v);
   p.out_t = reinterpret_cast<bf16*>(a->out_t);
   p.lse = a->lse;
-  {
-    static const int dbg_env = [] { const char* e = getenv("SIMVGB_ATTN_DEBUG"); return e ? atoi(e) : 0; }();
-    p.dbg = dbg_env;
-    p.ts = g_fwd_trace;
-  }
+  p.npairs = p.g.ntiles / 2;
+  p.n_full_items = a->B * a->H * p.npairs;
+  p.n_items = p.n_full_items + ((p.g.ntiles & 1) ? a->B * a->H : 0);
   CUtensorMap full, tail, text;
   if (make_attn_maps(&full, &tail, &text, p.g, a->qkv_v, a->qkv_t, 3 * D)) return -1;
   if (ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_kernel), kFwdSmem)) return -2;
-  dim3 grid(p.g.ntiles, a->H, a->B);
+  int grid = sm_count();
+  if (grid > p.n_items) grid = p.n_items;
   attn_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(full, tail, text, p);
   SIMVGB_CUDA(cudaGetLastError());
   return 0;
@@ -367,5 +445,3 @@ extern "C" int simvgb_attn_lse_stride(int Lv, int Lt) {
   simvgb::AttnGeom g = simvgb::make_attn_geom(1, 1, Lv, Lt, 64);
   return g.ntiles * simvgb::kTile;
 }
-
-extern "C" void simvgb_debug_attn_fwd_trace(long long* buf) { simvgb::g_fwd_trace = buf; }

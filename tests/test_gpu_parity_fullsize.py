@@ -75,8 +75,8 @@ def test_vit_large_224_train_step(lib):
 
 
 def test_vit_large_768_geometry_train_step(lib):
-    """ViT-L/16 at the 768x768 geometry of BASELINE configs[3] (Lv = 2305, L = 2325: 19 key tiles), 2 encoder layers, bs = 1."""
-    _check_train_step("vitl16_768_2layers", "large", 768, 16, 1, 3, 2, _LIM_L)
+    """ViT-L/16 at the 768x768 geometry of BASELINE configs[3] (Lv = 2305, L = 2325: 19 key tiles), 2 encoder layers, bs = 2."""
+    _check_train_step("vitl16_768_2layers", "large", 768, 16, 2, 3, 2, _LIM_L)
 
 
 def test_vit_large_24_layers_forward(lib):
@@ -89,7 +89,7 @@ def test_vit_large_24_layers_forward(lib):
     with torch.no_grad():
         feats = model.vis_enc(gb["img"], gb["ref_expr_inds"], gb["text_attention_mask"])
     rec = {"case": "vitl16_224_24layers_fwd"}
-    for tag, emu, flim in (("fp32", False, 2e-2), ("bf16emu", True, 4e-3)):
+    for tag, emu, flim in (("fp32", False, 2e-2), ("bf16emu", True, 8e-3)):
         ol, op, _, om = oracle_step(sd, cfg, vit, S, P, cb, emulate_bf16=emu, backward=False)
         with torch.no_grad():
             ofe = om._features(cb["img"], cb["ref_expr_inds"], cb["text_attention_mask"])
