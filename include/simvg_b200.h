@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SIMVGB_VERSION 100
+#define SIMVGB_VERSION 200
 
 int simvgb_version(void);
 const char* simvgb_last_error(void);
@@ -150,6 +150,11 @@ int simvgb_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
 /* Embedding assembly (torchscale VisionEmbedding / TextEmbedding / PositionalEmbedding, A.6-A.7;
  * Encoder.forward_embedding beit3_base.py:317-334 and the pad-zeroing at :367). */
 int simvgb_im2col_patch(const float* img, void* cols_bf16, int B, int S, int P, void* stream);
+/* Same patch matrix straight from the un-normalised uint8 [B,S,S,3] (HWC) image of the dataset pipeline: mmcv.imnormalize
+ * ((x - mean) / std per channel, BGR->RGB when to_rgb; simvg/datasets/pipelines/transforms.py:126-155) and the HWC->CHW
+ * transpose of the collate step (simvg/datasets/utils.py:24-52) fused into the im2col.  mean / std: host float[3]. */
+int simvgb_im2col_patch_u8(const void* img_u8, void* cols_bf16, int B, int S, int P, const float* mean, const float* std,
+                           int to_rgb, void* stream);
 int simvgb_embed_vision(const float* patch, const float* cls, const float* posA, float* xv, int B, int N, int D, void* stream);
 int simvgb_embed_text(const float* table, const int64_t* ids, const void* pad_u8, const float* posB, float* xt, int B,
                       int Lt, int D, void* stream);
@@ -158,15 +163,18 @@ int simvgb_embed_text(const float* table, const int64_t* ids, const void* pad_u8
  * grad_sumsq: device scalar holding sum(g^2) over ALL parameters (simvgb_sumsq accumulates into it); the clip
  * coefficient min(1, max_norm / (sqrt(sumsq) + 1e-6)) is evaluated on the device — no host sync. */
 int simvgb_sumsq(const float* g, int64_t n, float* out, void* stream);
+/* ema (optional, may be NULL): shadow weights updated in the same pass, ema = ema_decay * ema + (1 - ema_decay) * p_new —
+ * ExponentialMovingAverage.update_params (simvg/models/utils.py:148-173; decay = min(alpha, (1 + t) / (10 + t)) is the
+ * caller's). */
 int simvgb_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, float lr, float beta1,
                         float beta2, float eps, float weight_decay, int step, const float* grad_sumsq, float max_norm,
-                        void* stream);
-/* Same update with the step-dependent scalars taken from device memory: hyper = {lr, 1 - beta1^t, sqrt(1 - beta2^t)}
- * (fp32[3]).  The launch arguments are then step-invariant, so a whole train step can be captured in a CUDA graph and the
+                        float* ema, float ema_decay, void* stream);
+/* Same update with the step-dependent scalars taken from device memory: hyper = {lr, 1 - beta1^t, sqrt(1 - beta2^t),
+ * ema_decay} (fp32[4]).  The launch arguments are then step-invariant, so a whole train step can be captured in a CUDA graph and the
  * host only refreshes `hyper` before each replay. */
 int simvgb_adam_amsgrad_dev(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, const float* hyper,
                             float beta1, float beta2, float eps, float weight_decay, const float* grad_sumsq,
-                            float max_norm, void* stream);
+                            float max_norm, float* ema, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,16 +10,17 @@
 //   * persistent, one CTA per SM, each work item = TWO 128-query tiles (A, B) of one (sample, head) that share every K/V
 //     tile: the tensor pipe works on one tile while the MUFU/FMA pipes run the other tile's softmax (ping-pong), and K/V
 //     cross L2 -> smem once per 256 queries instead of once per 128;
-//   * one softmax thread owns one whole query row of a key tile (128 scores in registers, `setmaxnreg` moves registers from
-//     the two single-lane control warps to the softmax warpgroups): row max / row sum need no shuffle, no smem, no barrier;
+//   * sixteen softmax warps per CTA (eight per query tile: two per TMEM lane quarter, each thread owns one query row x 64 key
+//     columns, the two halves of a row exchange their maxima through 4 KB of shared memory): every SM sub-partition has four
+//     softmax warps in different phases, so the MUFU unit (the bound at head_dim 64: 16 exp2 / clk / SM against 8192 tensor
+//     MACs / clk) stays fed while other warps sit in TMEM loads, row-max chains or barrier waits;
 //   * S_X(j+1) is issued as soon as the softmax has pulled S_X(j) out of TMEM (P has its own TMEM columns), so scores are
 //     always waiting when a softmax warpgroup comes back; the next work item's Q / K / V loads and first S products overlap
 //     this item's epilogue;
 //   * P goes to TMEM as packed bf16 pairs (tcgen05.st) and is the A operand of O += P V (TS-form MMA); V is consumed
 //     MN-major straight from its token-major TMA tile; online softmax with lazy rescaling (O is touched only when a row
 //     maximum grows by more than 2^8).
-// Warp roles: 0 = TMA producer, 1 = tcgen05.mma issuer, 2-3 = idle (register donors), 4-7 = softmax of tile A, 8-11 = softmax
-// of tile B.  TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)  P_A [384,448)  P_B [448,512).
+// Warp roles: 0 = TMA producer, 1 / 2 = tcgen05.mma issuer of tile A / B, 3-10 = softmax of tile A, 11-18 = softmax of tile B.  TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)  P_A [384,448)  P_B [448,512).
 #include <stdlib.h>
 
 #include "attn_common.cuh"
@@ -33,11 +34,10 @@ namespace simvgb {
 #ifndef SIMVGB_FWD_KS
 #define SIMVGB_FWD_KS 3
 #endif
-constexpr int kFwdThreads = 384;
+constexpr int kFwdThreads = 608;
 constexpr int kKS = SIMVGB_FWD_KS;   // K ring depth = V ring depth
-constexpr int kFwdSmem = (2 + 2 * kKS) * kTileBytes + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int kFwdSmem = (2 + 2 * kKS) * kTileBytes + 1024 /*align*/ + 512 /*barriers*/ + 4096 /*row-max exchange*/;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr int kRegsCtl = 88, kRegsSoftmax = 208;   // (88 + 2 * 208) * 128 threads = 64,512 registers = 168 * 384
 
 struct AttnFwdParams {
   AttnGeom g;
@@ -66,8 +66,22 @@ __device__ __forceinline__ FwdItem decode_item(const AttnFwdParams& p, int it) {
   return w;
 }
 
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+// 32 lanes x 8 consecutive fp32 columns (the rare O-rescale path works in small pieces so it needs few registers while the
+// 64 scores of the tile are live)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void pair_sync(int id) {   // the two softmax warps that share a (tile, TMEM lane quarter)
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
 
 // exp2 of 32 scores (already in registers) -> 16 packed bf16 pairs, returns their fp32 sum.  x = s * log2e - m.
 template <bool kPoly>
@@ -109,6 +123,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   uint64_t* pv_done = s_full + 6;          // [2]  O_X += P_X(j) V(j) complete
   uint64_t* o_free = s_full + 8;           // [2]  epilogue X holds O_X in registers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 10);
+  float* xchg = reinterpret_cast<float*>(smem + (2 + 2 * kKS) * kTileBytes + 512);   // [tile 2][parity 2][half 2][128 rows]
 
   const AttnGeom& g = p.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,11 +138,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   if (threadIdx.x == 0) {
     for (int x = 0; x < 2; ++x) {
       mbar_init(&q_full[x], 1); mbar_init(&q_empty[x], 1);
-      mbar_init(&s_full[x], 1); mbar_init(&s_free[x], 4);     // one elected arrival per softmax warp
-      mbar_init(&p_full[x], 4); mbar_init(&pv_done[x], 1); mbar_init(&o_free[x], 4);
+      mbar_init(&s_full[x], 1); mbar_init(&s_free[x], 8);     // one elected arrival per softmax warp
+      mbar_init(&p_full[x], 8); mbar_init(&pv_done[x], 1); mbar_init(&o_free[x], 8);
     }
     for (int s = 0; s < kKS; ++s) {
-      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 2); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 2);   // both issuers release
     }
     fence_barrier_init();
   }
@@ -141,8 +156,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (uniform registers for UTCHMMA)
 
-  if (warp < 4) {
-    reg_dec<kRegsCtl>();
+  if (warp < 3) {
     if (warp == 0) {
       // ------------------------------ TMA producer ------------------------------
       if (lane == 0) {
@@ -174,172 +188,166 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
           for (int j = 1; j < nk; ++j) { load_k(j); load_v(j); }
         }
       }
-    } else if (warp == 1) {
-      // ------------------------------ MMA issuer: warp-uniform control flow, single-lane issue ------------------------------
+    } else {
+      // ------------------------------ MMA issuers: warp 1 drives tile A, warp 2 tile B ------------------------------
+      // One issuing warp per query tile: S_X(j+1) goes out the moment softmax X has pulled S_X(j) out of TMEM and P_X(j) V_j the
+      // moment P_X(j) is written, whatever the other tile is doing (a single issuer blocked on one tile's barrier delayed the
+      // other's products).  Warp-uniform control flow, single-lane issue.
+      const int x = warp - 1;
       const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);  // A = P (TMEM), B = V (MN-major)
-      const uint64_t dQ0 = umma_smem_desc(smem_u32(sQ), 16, 1024);
+      constexpr uint32_t kStep = kTileBytes >> 4;
+      const uint64_t dQ = umma_smem_desc(smem_u32(sQ), 16, 1024) + x * kStep;
       const uint64_t dK0 = umma_smem_desc(smem_u32(sK), 16, 1024);
       const uint64_t dV0 = umma_smem_desc(smem_u32(sV), 8192, 1024);
-      constexpr uint32_t kStep = kTileBytes >> 4;
-      uint32_t kc = 0, vc = 0, sc[2] = {0, 0}, pc[2] = {0, 0}, ic[2] = {0, 0};
+      const uint32_t tmS = tmem + 128 * x, tmO = tmem + 256 + 64 * x, tmP = tmem + 384 + 64 * x;
+      uint32_t kc = 0, vc = 0, sc = 0, pc = 0, ic = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
         const FwdItem w = decode_item(p, it);
-        const bool both = w.tB >= 0;
-        // S_X = Q_X K_j^T into TMEM columns [128 X, 128 X + 128); `last` also releases the Q_X buffer
-        auto issue_s = [&](int x, uint32_t kslot, bool last) {
-          mbar_wait(&s_free[x], (sc[x] & 1) ^ 1);             // softmax X has pulled the previous S_X out of TMEM
+        if (x == 1 && w.tB < 0) {
+          // single-tile item: tile B idles, but every K / V slot still needs this warp's release (the empty barriers count two)
+          for (int j = 0; j < nk; ++j) {
+            mbar_wait(&k_full[kc % kKS], (kc / kKS) & 1);
+            if (lane == 0) mbar_arrive(&k_empty[kc % kKS]);
+            ++kc;
+            mbar_wait(&v_full[vc % kKS], (vc / kKS) & 1);
+            if (lane == 0) mbar_arrive(&v_empty[vc % kKS]);
+            ++vc;
+          }
+          continue;
+        }
+        // S_X = Q_X K_j^T; `last` also releases the Q_X buffer
+        auto issue_s = [&](bool last) {
+          const uint32_t kslot = kc % kKS;
+          mbar_wait(&k_full[kslot], (kc / kKS) & 1);
+          mbar_wait(&s_free[x], (sc & 1) ^ 1);                // softmax X has pulled the previous S_X out of TMEM
           tc_fence_after();
-          const uint64_t dq = dQ0 + x * kStep, dk = dK0 + kslot * kStep;
+          const uint64_t dk = dK0 + kslot * kStep;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kHeadDim / 16; ++k) umma_f16_ss(tmem + 128 * x, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+            for (int k = 0; k < kHeadDim / 16; ++k) umma_f16_ss(tmS, dQ + 2 * k, dk + 2 * k, idesc_s, k > 0);
             umma_commit(&s_full[x]);
+            umma_commit(&k_empty[kslot]);
             if (last) umma_commit(&q_empty[x]);
           }
           __syncwarp();
-          ++sc[x];
+          ++sc;
+          ++kc;
         };
         // O_X (+)= P_X V_j
-        auto issue_pv = [&](int x, uint32_t vslot, bool first) {
-          mbar_wait(&p_full[x], pc[x] & 1);
-          if (first) mbar_wait(&o_free[x], (ic[x] & 1) ^ 1);  // the previous item's epilogue has read O_X
+        auto issue_pv = [&](bool first) {
+          const uint32_t vslot = vc % kKS;
+          mbar_wait(&v_full[vslot], (vc / kKS) & 1);
+          mbar_wait(&p_full[x], pc & 1);
+          if (first) mbar_wait(&o_free[x], (ic & 1) ^ 1);     // the previous item's epilogue has read O_X
           tc_fence_after();
           const uint64_t dv = dV0 + vslot * kStep;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kTile / 16; ++k)   // A = P[:, 16k .. 16k+16) = 8 packed TMEM columns
-              umma_f16_ts(tmem + 256 + 64 * x, tmem + 384 + 64 * x + 8 * k, dv + k * 128, idesc_o, (!first || k > 0) ? 1u : 0u);
+              umma_f16_ts(tmO, tmP + 8 * k, dv + k * 128, idesc_o, (!first || k > 0) ? 1u : 0u);
             umma_commit(&pv_done[x]);
-          }
-          __syncwarp();
-          ++pc[x];
-        };
-        uint32_t kslot = kc % kKS;
-        mbar_wait(&q_full[0], ic[0] & 1);
-        mbar_wait(&k_full[kslot], (kc / kKS) & 1);
-        issue_s(0, kslot, nk == 1);
-        if (both) {
-          mbar_wait(&q_full[1], ic[1] & 1);
-          issue_s(1, kslot, nk == 1);
-        }
-        if (elect_one()) umma_commit(&k_empty[kslot]);
-        __syncwarp();
-        ++kc;
-        for (int j = 0; j < nk; ++j) {
-          const bool more = j + 1 < nk;
-          const uint32_t vslot = vc % kKS;
-          kslot = kc % kKS;
-          if (more) {
-            mbar_wait(&k_full[kslot], (kc / kKS) & 1);
-            issue_s(0, kslot, j + 2 == nk);
-          }
-          mbar_wait(&v_full[vslot], (vc / kKS) & 1);
-          issue_pv(0, vslot, j == 0);
-          if (both) {
-            if (more) issue_s(1, kslot, j + 2 == nk);
-            issue_pv(1, vslot, j == 0);
-          }
-          if (elect_one()) {
-            if (more) umma_commit(&k_empty[kslot]);
             umma_commit(&v_empty[vslot]);
           }
           __syncwarp();
-          if (more) ++kc;
+          ++pc;
           ++vc;
+        };
+        mbar_wait(&q_full[x], ic & 1);
+        issue_s(nk == 1);
+        for (int j = 0; j < nk; ++j) {
+          if (j + 1 < nk) issue_s(j + 2 == nk);
+          issue_pv(j == 0);
         }
-        ++ic[0];
-        if (both) ++ic[1];
+        ++ic;
       }
     }
   } else {
-    reg_inc<kRegsSoftmax>();
-    // ------------------------------ softmax + epilogue: thread = one query row of tile X ------------------------------
-    const int x = (warp - 4) >> 2;
+// ------------------------------ softmax + epilogue: thread = (query row of tile X, 64-key half) ------------------------------
+    const int k16 = warp - 3;
+    const int x = k16 >> 3;
+    const int half = (k16 >> 2) & 1;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
+    const int bar_id = 1 + x * 4 + quarter;
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-    const uint32_t tmS = tmem + 128 * x + lane_base, tmO = tmem + 256 + 64 * x + lane_base, tmP = tmem + 384 + 64 * x + lane_base;
+    const uint32_t tmS = tmem + 128 * x + lane_base + 64 * half;
+    const uint32_t tmO = tmem + 256 + 64 * x + lane_base + 32 * half;
+    const uint32_t tmP = tmem + 384 + 64 * x + lane_base + 32 * half;
+    float* xrow = xchg + x * 512;
     uint32_t sc = 0, pc = 0;
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       const FwdItem w = decode_item(p, it);
       const int qt = x == 0 ? w.tA : w.tB;
       if (qt < 0) continue;
-      // validity bits of the (at most two) partial key tiles of sample b: bit c of word [t][k] = key t*128 + 32k + c is a real,
-      // unpadded token.  Every lane tests 8 positions; one ballot per word (warp-uniform result).
-      uint32_t mk[2][4];
+      // validity bits of this half of the (at most two) partial key tiles of sample b: bit c of word [t][k] = key
+      // t*128 + 64*half + 32k + c is a real, unpadded token.  One ballot per word (warp-uniform result).
+      uint32_t mk[2][2];
 #pragma unroll
       for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int v = (g.nfull + t) * kTile + 32 * k + lane;
+        for (int k = 0; k < 2; ++k) {
+          const int v = (g.nfull + t) * kTile + 64 * half + 32 * k + lane;
           bool ok = v < g.Lv;
           if (!ok && v >= g.T0 && v < g.T0 + g.Lt) ok = (p.pad == nullptr) || (p.pad[w.b * g.Lt + (v - g.T0)] == 0);
           mk[t][k] = __ballot_sync(0xffffffffu, ok);
         }
-      float m = -INFINITY, l = 0.f;
+      float m = -INFINITY, l = 0.f;   // l: partial row sum over this thread's columns
       for (int j = 0; j < nk; ++j) {
         mbar_wait(&s_full[x], sc & 1);
-        ++sc;
         tc_fence_after();
-        uint32_t s0[32], s1[32], s2[32], s3[32];
+        uint32_t s0[32], s1[32];
         tmem_ld32(tmS, s0);
         tmem_ld32(tmS + 32, s1);
-        tmem_ld32(tmS + 64, s2);
-        tmem_ld32(tmS + 96, s3);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[x]);   // scores are in registers: the MMA warp may overwrite S_X
-        const bool partial = j >= g.nfull;
-        if (partial) {
+        if (j >= g.nfull) {
           const int t = j - g.nfull;
+          const uint32_t ba = mk[t][0], bb = mk[t][1];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            if (!((mk[t][0] >> i) & 1u)) s0[i] = 0xff800000u;   // -inf
-            if (!((mk[t][1] >> i) & 1u)) s1[i] = 0xff800000u;
-            if (!((mk[t][2] >> i) & 1u)) s2[i] = 0xff800000u;
-            if (!((mk[t][3] >> i) & 1u)) s3[i] = 0xff800000u;
+            if (!((ba >> i) & 1u)) s0[i] = 0xff800000u;   // -inf
+            if (!((bb >> i) & 1u)) s1[i] = 0xff800000u;
           }
         }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s2[i]), __uint_as_float(s3[i])));
+        for (int i = 0; i < 16; ++i) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s0[i + 16])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s1[i]), __uint_as_float(s1[i + 16])));
         }
-        const float mx = fmaxf(mx0, mx1) * kLog2e;
+        mx2 = fmaxf(mx0, mx1);
+        float* xm = xrow + (sc & 1) * 256;
+        xm[half * 128 + r] = mx2;
+        pair_sync(bar_id);
+        mx3 = fmaxf(mx2, xm[(half ^ 1) * 128 + r]);
+        ++sc;
+        const float mx = mx3 * kLog2e;
         const bool need = mx > m + 8.0f;       // lazy rescale threshold (log2 units); true on the first tile
         const float m_use = need ? mx : m;
         const float alpha = need ? ex2_approx(m - m_use) : 1.0f;
+        const float neg_m = -m_use;
+        uint32_t pk[16];
+        // the first 32 exponentials need neither the P buffer nor O: they run while P_X(j-1) V_(j-1) is still on the tensor pipe
+        float sum = exp_chunk<(SIMVGB_FWD_POLY > 0)>(s0, pk, neg_m);
         mbar_wait(&pv_done[x], (pc & 1) ^ 1);  // P_X buffer free, O_X complete up to tile j-1
+        tc_fence_after();
         if (j > 0 && __any_sync(0xffffffffu, need)) {
-          tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmO + 32 * c, v);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[8];
+            tmem_ld8(tmO + 8 * c, v);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st32(tmO + 32 * c, v);
+            for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st8(tmO + 8 * c, v);
           }
-          tmem_wait_st();
         }
-        const float neg_m = -m_use;
-        float sum = 0.f;
-        uint32_t pk[16];
-        if (partial) {   // masked scores are -inf: MUFU handles them, the FMA-pipe exp2 does not
-          sum += exp_chunk<false>(s0, pk, neg_m); tmem_st16(tmP, pk);
-          sum += exp_chunk<false>(s1, pk, neg_m); tmem_st16(tmP + 16, pk);
-          sum += exp_chunk<false>(s2, pk, neg_m); tmem_st16(tmP + 32, pk);
-          sum += exp_chunk<false>(s3, pk, neg_m); tmem_st16(tmP + 48, pk);
-        } else {
-          sum += exp_chunk<(SIMVGB_FWD_POLY > 0)>(s0, pk, neg_m); tmem_st16(tmP, pk);
-          sum += exp_chunk<(SIMVGB_FWD_POLY > 0)>(s1, pk, neg_m); tmem_st16(tmP + 16, pk);
-          sum += exp_chunk<(SIMVGB_FWD_POLY > 0)>(s2, pk, neg_m); tmem_st16(tmP + 32, pk);
-          sum += exp_chunk<(SIMVGB_FWD_POLY > 0)>(s3, pk, neg_m); tmem_st16(tmP + 48, pk);
-        }
+        tmem_st16(tmP, pk);
+        sum += exp_chunk<(SIMVGB_FWD_POLY > 0)>(s1, pk, neg_m);
+        tmem_st16(tmP + 16, pk);
         tmem_wait_st();
         l = l * alpha + sum;
         m = m_use;
@@ -349,11 +357,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
         ++pc;
       }
       // ------------------------------ epilogue ------------------------------
+      float* xs = xrow + (sc & 1) * 256;      // the buffer tile nk would use: free (tile nk-2's readers passed tile nk-1's barrier)
+      xs[half * 128 + r] = l;
+      pair_sync(bar_id);
+      l += xs[(half ^ 1) * 128 + r];
       mbar_wait(&pv_done[x], (pc - 1) & 1);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
+      uint32_t o0[32];
       tmem_ld32(tmO, o0);
-      tmem_ld32(tmO + 32, o1);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
@@ -364,22 +375,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
       else if (qv >= g.T0 && qv < g.T0 + g.Lt) dst = p.out_t + ((long long)w.b * g.Lt + (qv - g.T0)) * g.D + w.h * kHeadDim;
       const float inv = 1.0f / l;
       if (dst != nullptr) {
-        uint4* o = reinterpret_cast<uint4*>(dst);
+        uint4* o = reinterpret_cast<uint4*>(dst + 32 * half);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
+        for (int q4 = 0; q4 < 4; ++q4)
           o[q4] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * q4]) * inv, __uint_as_float(o0[8 * q4 + 1]) * inv),
                              pack_bf16x2(__uint_as_float(o0[8 * q4 + 2]) * inv, __uint_as_float(o0[8 * q4 + 3]) * inv),
                              pack_bf16x2(__uint_as_float(o0[8 * q4 + 4]) * inv, __uint_as_float(o0[8 * q4 + 5]) * inv),
                              pack_bf16x2(__uint_as_float(o0[8 * q4 + 6]) * inv, __uint_as_float(o0[8 * q4 + 7]) * inv));
-          o[4 + q4] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * q4]) * inv, __uint_as_float(o1[8 * q4 + 1]) * inv),
-                                 pack_bf16x2(__uint_as_float(o1[8 * q4 + 2]) * inv, __uint_as_float(o1[8 * q4 + 3]) * inv),
-                                 pack_bf16x2(__uint_as_float(o1[8 * q4 + 4]) * inv, __uint_as_float(o1[8 * q4 + 5]) * inv),
-                                 pack_bf16x2(__uint_as_float(o1[8 * q4 + 6]) * inv, __uint_as_float(o1[8 * q4 + 7]) * inv));
-        }
       }
       // positions of the virtual axis that are not tokens get LSE = +inf: the backward then computes P = exp2(S - inf) = 0
       // for them without any query-side masking
-      if (p.lse != nullptr)
+      if (p.lse != nullptr && half == 0)
         p.lse[((long long)w.b * g.H + w.h) * (g.ntiles * kTile) + qv] = dst != nullptr ? m + log2f(l) : INFINITY;
     }
   }

@@ -2,6 +2,8 @@
 // Replaces clip_grad_norm_ + torch.optim.Adam(amsgrad=True).step() (/root/reference/simvg/apis/train.py:81-83,
 // /root/reference/simvg/core/optimizer.py:52-68; hyper-parameters configs/single/ViT-base/refcoco/refcoco_onestage.py:107-123),
 // i.e. hundreds of small eager kernels, by two streaming passes: sum of squares, then the update (36 B / parameter).
+// The exponential moving average of the weights (/root/reference/simvg/models/utils.py:148-173, called after every optimiser
+// step at apis/train.py:85-86: a Python loop over the whole state dict) rides along in the update pass when enabled.
 #include "common.cuh"
 #include "simvg_b200.h"
 
@@ -33,11 +35,13 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
 __global__ void adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                     float* __restrict__ v, float* __restrict__ vmax, long long n, float lr, float beta1,
                                     float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-                                    const float* __restrict__ sumsq, float max_norm, const float* __restrict__ hyper) {
+                                    const float* __restrict__ sumsq, float max_norm, const float* __restrict__ hyper,
+                                    float* __restrict__ ema, float ema_decay) {
   if (hyper != nullptr) {   // step-dependent scalars read from the device: the launch can live inside a CUDA graph
     lr = __ldg(hyper);
     bc1 = __ldg(hyper + 1);
     bc2_sqrt = __ldg(hyper + 2);
+    ema_decay = __ldg(hyper + 3);
   }
   float coef = 1.0f;
   if (sumsq != nullptr && max_norm > 0.f) coef = fminf(1.0f, max_norm / (sqrtf(__ldg(sumsq)) + 1e-6f));
@@ -60,6 +64,14 @@ __global__ void adam_amsgrad_kernel(float* __restrict__ p, const float* __restri
     }
     SIMVGB_ADAM1(x) SIMVGB_ADAM1(y) SIMVGB_ADAM1(z) SIMVGB_ADAM1(w)
     reinterpret_cast<float4*>(p)[i] = pp;
+    if (ema != nullptr) {   // ExponentialMovingAverage.update_params fused in: shadow = d * shadow + (1 - d) * p_new  (+8 B / parameter)
+      float4 ee = reinterpret_cast<float4*>(ema)[i];
+      ee.x = ema_decay * ee.x + (1.f - ema_decay) * pp.x;
+      ee.y = ema_decay * ee.y + (1.f - ema_decay) * pp.y;
+      ee.z = ema_decay * ee.z + (1.f - ema_decay) * pp.z;
+      ee.w = ema_decay * ee.w + (1.f - ema_decay) * pp.w;
+      reinterpret_cast<float4*>(ema)[i] = ee;
+    }
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
     reinterpret_cast<float4*>(vmax)[i] = xx;
@@ -71,6 +83,7 @@ __global__ void adam_amsgrad_kernel(float* __restrict__ p, const float* __restri
     v[i] = beta2 * v[i] + (1.f - beta2) * gr * gr;
     vmax[i] = fmaxf(vmax[i], v[i]);
     p[i] -= step * m[i] / (sqrtf(vmax[i]) / bc2_sqrt + eps);
+    if (ema != nullptr) ema[i] = ema_decay * ema[i] + (1.f - ema_decay) * p[i];
   }
 }
 
@@ -93,7 +106,7 @@ extern "C" int simvgb_sumsq(const float* g, int64_t n, float* out, void* stream)
 
 extern "C" int simvgb_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, float lr,
                                    float beta1, float beta2, float eps, float weight_decay, int step,
-                                   const float* grad_sumsq, float max_norm, void* stream) {
+                                   const float* grad_sumsq, float max_norm, float* ema, float ema_decay, void* stream) {
   SIMVGB_CHECK(p && g && m && v && vmax, "simvgb_adam_amsgrad: null pointer");
   SIMVGB_CHECK(step >= 1, "simvgb_adam_amsgrad: step must be >= 1");
   SIMVGB_CHECK(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -107,14 +120,14 @@ extern "C" int simvgb_adam_amsgrad(float* p, const float* g, float* m, float* v,
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   adam_amsgrad_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      p, g, m, v, vmax, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_sumsq, max_norm, nullptr);
+      p, g, m, v, vmax, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_sumsq, max_norm, nullptr, ema, ema_decay);
   SIMVGB_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int simvgb_adam_amsgrad_dev(float* p, const float* g, float* m, float* v, float* vmax, int64_t n,
                                        const float* hyper, float beta1, float beta2, float eps, float weight_decay,
-                                       const float* grad_sumsq, float max_norm, void* stream) {
+                                       const float* grad_sumsq, float max_norm, float* ema, void* stream) {
   SIMVGB_CHECK(p && g && m && v && vmax && hyper, "simvgb_adam_amsgrad_dev: null pointer");
   SIMVGB_CHECK(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                  reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(vmax)) & 15) == 0,
@@ -125,7 +138,7 @@ extern "C" int simvgb_adam_amsgrad_dev(float* p, const float* g, float* m, float
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   adam_amsgrad_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      p, g, m, v, vmax, n, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, grad_sumsq, max_norm, hyper);
+      p, g, m, v, vmax, n, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, grad_sumsq, max_norm, hyper, ema, 0.f);
   SIMVGB_CUDA(cudaGetLastError());
   return 0;
 }

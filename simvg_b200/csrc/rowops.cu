@@ -682,6 +682,41 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, bf16* __restr
   store8(cols + e, v);
 }
 
+// The same im2col fed from the image as the dataset pipeline holds it BEFORE `Normalize`: uint8 [B,S,S,3] (HWC, cv2 channel
+// order).  mmcv.imnormalize (/root/reference/simvg/datasets/pipelines/transforms.py:126-155: optional BGR->RGB swap, then
+// (x - mean) * (1 / std) in fp32) and the HWC -> CHW transpose of DefaultFormatBundle are applied on the fly, so a batch
+// crosses PCIe and HBM as 1 byte per sample instead of 4.  One thread = 8 consecutive pixels of one patch row, all channels.
+__global__ void im2col_patch_u8_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ cols, int B, int S, int P,
+                                       float m0, float m1, float m2, float i0, float i1, float i2, int to_rgb) {
+  const int G = S / P;
+  const long long K = 3LL * P * P;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = P * P / 8;                    // threads per patch
+  const long long total = (long long)B * G * G * per_row;
+  if (idx >= total) return;
+  const long long row = idx / per_row;
+  const int k = (idx % per_row) * 8;               // ky * P + kx
+  const int ky = k / P, kx = k % P;
+  const int n = row % (G * G);
+  const long long b = row / (G * G);
+  const int gy = n / G, gx = n % G;
+  const uint8_t* src = img + ((b * S + (gy * P + ky)) * (long long)S + gx * P + kx) * 3;   // 24 contiguous bytes, 8-byte aligned
+  uint2 raw[3];
+  raw[0] = __ldg(reinterpret_cast<const uint2*>(src));
+  raw[1] = __ldg(reinterpret_cast<const uint2*>(src) + 1);
+  raw[2] = __ldg(reinterpret_cast<const uint2*>(src) + 2);
+  const uint8_t* px = reinterpret_cast<const uint8_t*>(raw);
+  const float mean[3] = {m0, m1, m2}, inv[3] = {i0, i1, i2};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int sc = to_rgb ? 2 - c : c;               // output channel c reads stored channel sc
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ((float)px[3 * i + sc] - mean[c]) * inv[c];
+    store8(cols + row * K + (long long)c * P * P + k, v);
+  }
+}
+
 static int ln_geometry(int C, int* W, int* rpb) {
   if (C % 256 != 0 || C > 8192) return -1;
   *W = C / 256;
@@ -855,6 +890,21 @@ extern "C" int simvgb_embed_text(const float* table, const int64_t* ids, const v
   if (total == 0) return 0;
   assemble_text_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       table, reinterpret_cast<const long long*>(ids), reinterpret_cast<const unsigned char*>(pad), posB, xt, B, Lt, D);
+  SIMVGB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int simvgb_im2col_patch_u8(const void* img_u8, void* cols, int B, int S, int P, const float* mean, const float* std,
+                                      int to_rgb, void* stream) {
+  SIMVGB_CHECK(img_u8 && cols && mean && std, "simvgb_im2col_patch_u8: null pointer");
+  SIMVGB_CHECK(P % 8 == 0 && S % P == 0, "simvgb_im2col_patch_u8: need P %% 8 == 0 and S %% P == 0 (S=%d P=%d)", S, P);
+  SIMVGB_CHECK((reinterpret_cast<uintptr_t>(img_u8) & 7) == 0, "simvgb_im2col_patch_u8: image must be 8-byte aligned");
+  SIMVGB_CHECK(std[0] != 0.f && std[1] != 0.f && std[2] != 0.f, "simvgb_im2col_patch_u8: zero std");
+  const long long total = (long long)B * (S / P) * (S / P) * (P * P / 8);
+  // 1 / std evaluated in double and rounded once, as mmcv.imnormalize does (stdinv = 1 / np.float64(std))
+  im2col_patch_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint8_t*>(img_u8), (bf16*)cols, B, S, P, mean[0], mean[1], mean[2], (float)(1.0 / (double)std[0]),
+      (float)(1.0 / (double)std[1]), (float)(1.0 / (double)std[2]), to_rgb);
   SIMVGB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -101,9 +101,9 @@ def _lib_setup():
         lib.simvgb_embed_text.argtypes = [L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_int, L.c_int, L.c_int, L.c_vp]
         lib.simvgb_sumsq.argtypes = [L.c_vp, L.c_i64, L.c_vp, L.c_vp]
         lib.simvgb_adam_amsgrad.argtypes = [L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_i64, L.c_f32, L.c_f32, L.c_f32,
-                                            L.c_f32, L.c_f32, L.c_int, L.c_vp, L.c_f32, L.c_vp]
+                                            L.c_f32, L.c_f32, L.c_int, L.c_vp, L.c_f32, L.c_vp, L.c_f32, L.c_vp]
         lib.simvgb_adam_amsgrad_dev.argtypes = [L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_i64, L.c_vp, L.c_f32, L.c_f32,
-                                                L.c_f32, L.c_f32, L.c_vp, L.c_f32, L.c_vp]
+                                                L.c_f32, L.c_f32, L.c_vp, L.c_f32, L.c_vp, L.c_vp]
         lib._simvgb_typed = True
     return lib
 
@@ -329,6 +329,21 @@ def im2col_patch(img, P):
     return cols
 
 
+def im2col_patch_u8(img_u8, P, mean, std, to_rgb=True):
+    """uint8 [B,S,S,3] (HWC) image -> normalised bf16 patch matrix [B*N, 3*P*P] (Normalize + transpose + im2col fused)."""
+    L.require_device(img_u8)
+    lib = _lib_setup()
+    B, S, S2, C = img_u8.shape
+    assert img_u8.dtype == torch.uint8 and C == 3 and S == S2 and img_u8.is_contiguous()
+    cols = torch.empty(B * (S // P) ** 2, 3 * P * P, device=img_u8.device, dtype=bf16)
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    sd = (ctypes.c_float * 3)(*[float(v) for v in std])
+    L.check(lib.simvgb_im2col_patch_u8(L.c_vp(img_u8.data_ptr()), L.c_vp(cols.data_ptr()), B, S, P, m, sd, int(bool(to_rgb)),
+                                       L.c_vp(_stream())), "im2col_patch_u8")
+    _launches[0] += 1
+    return cols
+
+
 def embed_vision(patch, cls, posA, B, N, D):
     lib = _lib_setup()
     xv = torch.empty(B * (N + 1), D, device=patch.device, dtype=f32)
@@ -353,18 +368,20 @@ def sumsq(g, out):
     _launches[0] += 1
 
 
-def adam_amsgrad(p, g, m, v, vmax, lr, beta1, beta2, eps, weight_decay, step, grad_sumsq=None, max_norm=0.0):
+def adam_amsgrad(p, g, m, v, vmax, lr, beta1, beta2, eps, weight_decay, step, grad_sumsq=None, max_norm=0.0, ema=None,
+                 ema_decay=0.0):
+    """Clip (global norm from `grad_sumsq`) + Adam(amsgrad) on flat fp32 buffers; `ema`: shadow weights updated in the same pass."""
     lib = _lib_setup()
     L.check(lib.simvgb_adam_amsgrad(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), vmax.data_ptr(), p.numel(),
-                                    lr, beta1, beta2, eps, weight_decay, step, _p(grad_sumsq), max_norm, _stream()),
-            "adam_amsgrad")
+                                    lr, beta1, beta2, eps, weight_decay, step, _p(grad_sumsq), max_norm, _p(ema), ema_decay,
+                                    _stream()), "adam_amsgrad")
     _launches[0] += 1
 
 
-def adam_amsgrad_dev(p, g, m, v, vmax, hyper, beta1, beta2, eps, weight_decay, grad_sumsq=None, max_norm=0.0):
-    """Adam(amsgrad) with {lr, 1-beta1^t, sqrt(1-beta2^t)} read from the device tensor `hyper` (graph-capturable)."""
+def adam_amsgrad_dev(p, g, m, v, vmax, hyper, beta1, beta2, eps, weight_decay, grad_sumsq=None, max_norm=0.0, ema=None):
+    """Adam(amsgrad) with {lr, 1-beta1^t, sqrt(1-beta2^t), ema_decay} read from the device tensor `hyper` (graph-capturable)."""
     lib = _lib_setup()
     L.check(lib.simvgb_adam_amsgrad_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), vmax.data_ptr(), p.numel(),
-                                        hyper.data_ptr(), beta1, beta2, eps, weight_decay, _p(grad_sumsq), max_norm,
+                                        hyper.data_ptr(), beta1, beta2, eps, weight_decay, _p(grad_sumsq), max_norm, _p(ema),
                                         _stream()), "adam_amsgrad_dev")
     _launches[0] += 1

@@ -10,8 +10,15 @@ class BaseModel(nn.Module, metaclass=ABCMeta):
         super().__init__()
         self.fp16_enabled = False
 
+    @staticmethod
+    def image_hw(img):
+        """(H, W) of a batch given as float [B,3,H,W] (the reference's collated input) or as raw uint8 [B,H,W,3] (the GPU input
+        path: Normalize + transpose fused into the patch embedding, see BEIT3.input_norm)."""
+        import torch
+        return tuple(img.shape[1:3]) if img.dtype == torch.uint8 else tuple(img.shape[-2:])
+
     def add_batch_input_shape(self, img, img_metas):
-        shape = tuple(img.size()[-2:])
+        shape = self.image_hw(img)
         for m in img_metas:
             m["batch_input_shape"] = shape
 

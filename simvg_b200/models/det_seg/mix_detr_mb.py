@@ -25,7 +25,8 @@ class MIXDETRMB(OneStageModel):
         return self.vis_enc(img, ref_expr_inds, text_attention_mask)
 
     def _features(self, img, ref_expr_inds, text_attention_mask):
-        B, _, H, W = img.shape
+        B = img.shape[0]
+        H, W = self.image_hw(img)
         img_feat, text_feat, cls_feat = self.extract_visual_language(img, ref_expr_inds, text_attention_mask)
         h, w = H // self.patch_size, W // self.patch_size
         x_mm = img_feat.reshape(B, h, w, img_feat.shape[-1]).permute(0, 3, 1, 2)   # [B, D, h, w], channels-last strides

@@ -151,6 +151,13 @@ class BEIT3(nn.Module):
         self._flat = None
         self._attn_ws = {}
         self._ddp = None   # set by simvg_b200.optim.FlatDDP: gradient ranges are all-reduced as they become final
+        # Data-parallel runs exchange the text-embedding gradient as (ids, rows) instead of the dense [vocab, D] table:
+        # FlatDDP sets "defer", the backward then leaves the compact form here (simvg_b200/optim.py::_exchange_text_rows).
+        self.sparse_text_grad = {"defer": False, "ids": None, "rows": None}
+        # GPU input path: a uint8 [B,S,S,3] batch (the dataset pipeline's image before `Normalize`) is normalised inside the
+        # patch-embedding prologue with these constants — the reference's img_norm_cfg
+        # (/root/reference/configs/_base_/datasets/detection/refcoco-unc.py:5-6; pipelines/transforms.py:126-155).
+        self.input_norm = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=True)
         if isinstance(pretrain, str):
             self.load_model_and_may_interpolate(pretrain)
         if freeze_layer >= 0:
@@ -296,7 +303,11 @@ def _drop_path_scales(mod, B, device):
 def encoder_forward(mod, image, ids, pad_mask, save):
     cfg = mod.cfg
     D, H, F, P, eps = cfg["embed_dim"], cfg["heads"], cfg["ffn_dim"], cfg["patch_size"], cfg["eps"]
-    B, _, S, S2 = image.shape
+    raw_u8 = image.dtype == torch.uint8
+    if raw_u8:
+        B, S, S2, _ = image.shape
+    else:
+        B, _, S, S2 = image.shape
     assert S == cfg["img_size"] and S2 == cfg["img_size"], \
         "Input image size (%d*%d) doesn't match model (%d*%d)." % (S, S2, cfg["img_size"], cfg["img_size"])  # A.6
     N = (S // P) ** 2
@@ -308,9 +319,11 @@ def encoder_forward(mod, image, ids, pad_mask, save):
     glob, layers = mod._views(need_grad=save)
     pad_u8 = None if pad_mask is None else (pad_mask != 0).to(torch.uint8).contiguous()
     ids = ids.contiguous().long()
-    image = image.contiguous().float()
-
-    cols = K.im2col_patch(image, P)
+    if raw_u8:
+        nrm = mod.input_norm
+        cols = K.im2col_patch_u8(image.contiguous(), P, nrm["mean"], nrm["std"], nrm.get("to_rgb", True))
+    else:
+        cols = K.im2col_patch(image.contiguous().float(), P)
     patch = K.gemm(cols, glob["proj_w"][1].view(D, 3 * P * P), B * N, D, 3 * P * P, epilogue=K.EPI_F32, bias=glob["proj_b"][0])
     x = [K.embed_vision(patch, glob["cls_token"][0], glob["posA"][0], B, N, D),
          K.embed_text(glob["text_embed"][0], ids, pad_u8, glob["posB"][0], B, Lt, D)]
@@ -440,10 +453,12 @@ def encoder_backward(mod, ctx, dxv, dxt):
                          dres_out=dres[g])
         del dh
         ctx["layers"][li] = None  # release this layer's activations
-        if ddp is not None and li > 0:
+        if li > 0:
             # every gradient of layer li is final now (its fc2 bias was written by layer li+1's LN1 backward)
             i0 = mod._n_global + li * 2 * nf
             i1 = i0 + 2 * nf
+            _zero_frozen(fb, i0, i1)   # BEFORE the range is handed to the (asynchronous, in-place) all-reduce
+        if ddp is not None and li > 0:
             ddp.on_encoder_range_done(fb.offsets[i0], fb.offsets[i1] if i1 < len(fb.offsets) else fb.numel)
     # ---- embeddings (Encoder.forward_embedding, beit3_base.py:317-334 ; VisionEmbedding / TextEmbedding A.6-A.7)
     dv = dres[0].view(B, Lv, D)
@@ -456,13 +471,22 @@ def encoder_backward(mod, ctx, dxv, dxt):
     if ctx["pad"] is not None:
         dt = dt * (1.0 - ctx["pad"].view(B, Lt, 1).float())
     glob["posB"][2][2:2 + Lt].add_(dt.sum(0))
-    glob["text_embed"][2].index_add_(0, ctx["ids"].reshape(-1), dt.reshape(B * Lt, D))
-    for i, p in enumerate(fb.params):
-        if not p.requires_grad:
-            fb.grad_of(i).zero_()
+    st = mod.sparse_text_grad
+    if st["defer"]:   # data parallel: ranks all-gather these <= B*Lt rows instead of all-reducing the dense table
+        st["ids"], st["rows"] = ctx["ids"].reshape(-1), dt.reshape(B * Lt, D).contiguous()
+    else:
+        glob["text_embed"][2].index_add_(0, ctx["ids"].reshape(-1), dt.reshape(B * Lt, D))
+    _zero_frozen(fb, 0, mod._n_global + 2 * nf)
     if ddp is not None:   # layer 0 + the embedding / final-LN parameters at the front of the buffer
         i1 = mod._n_global + 2 * nf
         ddp.on_encoder_range_done(0, fb.offsets[i1] if i1 < len(fb.offsets) else fb.numel)
+
+
+def _zero_frozen(fb, i0, i1):
+    """Frozen parameters (BEIT3(freeze_layer=k), beit3.py:78-90) keep zero gradients; the optimiser skips them entirely."""
+    for i in range(i0, min(i1, len(fb.params))):
+        if not fb.params[i].requires_grad:
+            fb.grad_of(i).zero_()
 
 
 class _EncoderFn(torch.autograd.Function):

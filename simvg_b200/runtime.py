@@ -1,11 +1,17 @@
-"""Whole-train-step CUDA graph (B200-first runtime piece; the reference has no counterpart — its step is ~4000 eager
-launches driven from Python, /root/reference/simvg/apis/train.py:75-83).
+"""Whole-train-step CUDA graphs (B200-first runtime piece; the reference has no counterpart — its step is ~4000 eager
+launches driven from Python, /root/reference/simvg/apis/train.py:75-86).
 
-One SimVG train step here is ~5000 kernel launches, ~2000 of them tiny fp32 ops of the DETR head / DWBD losses whose
-launch overhead the CPU cannot hide; capturing fwd + losses + bwd + gradient all-reduce + clip + Adam once and replaying
-the graph removes that host cost.  Everything inside is step-invariant: inputs are copied into static buffers, the
-optimiser reads its step-dependent scalars from device memory (FusedAdamAMSGrad.advance), DropPath draws from the
-graph-registered CUDA generator, and the model code performs no host synchronisation on the REC path.
+One SimVG train step here is thousands of kernel launches, many of them tiny fp32 ops of the DETR head / DWBD losses whose
+launch overhead the CPU cannot hide; capturing them once and replaying removes that host cost.  Everything inside is
+step-invariant: inputs are copied into static buffers, the optimiser reads its step-dependent scalars from device memory
+(FusedAdamAMSGrad.advance), DropPath draws from the graph-registered CUDA generator, and the model code performs no host
+synchronisation on the REC path.
+
+  1 GPU : ONE graph  = zero_grad + forward + losses + backward + clip + Adam(+EMA).
+  N GPUs: TWO graphs = [zero_grad + forward + losses + backward]  ->  gradient exchange (NCCL, launched between the
+          graphs on the same stream: all-reduce of the flat gradient ranges + all-gather of the text-embedding rows)  ->
+          [clip + Adam(+EMA)].  No collective is captured (capturing them hung in round 1), every rank replays exactly the
+          launch sequence the 1-GPU number is quoted on, and the only exposed communication is one ~0.7 GB all-reduce.
 """
 import torch
 
@@ -15,32 +21,35 @@ from simvg_b200 import kernels as K
 class GraphedTrainStep:
     """step = GraphedTrainStep(model, optimizer, ddp=None); losses, preds = step(img, ids, img_metas, mask, gt_boxes)
 
-    img [B,3,S,S] fp32, ids / mask [B,Lt] int64, gt_boxes [B,4] (xyxy pixels) — host (ideally pinned) or device tensors.
-    The first call runs `warmup` eager steps' worth of allocator warm-up on a side stream and captures; later calls with
-    the same shapes and image sizes replay.  Returned tensors are the graph's static outputs (overwritten by the next call).
-    """
+    img [B,3,S,S] fp32 (or uint8 [B,S,S,3] when the encoder was given `input_norm`), ids / mask [B,Lt] int64, gt_boxes [B,4]
+    (xyxy pixels) — host (ideally pinned) or device tensors.  The first call runs `warmup` forward+backward passes WITHOUT
+    an optimiser step (allocator / workspace / NCCL warm-up: parameters, Adam moments and the step count are untouched, so
+    the training trajectory equals the eager loop's) and captures; later calls with the same shapes and image sizes replay.
+    A new batch shape re-captures (again without touching the optimiser state).  Returned tensors are the graph's static
+    outputs (overwritten by the next call)."""
 
-    def __init__(self, model, optimizer, ddp=None, warmup=2):
-        self.model, self.opt, self.ddp, self.warmup = model, optimizer, ddp, warmup
-        self.graph = None
+    def __init__(self, model, optimizer, ddp=None, warmup=1):
+        self.model, self.opt, self.warmup = model, optimizer, max(1, int(warmup))
+        self.ddp = ddp if (ddp is not None and ddp.world > 1) else None
+        if self.ddp is not None and not self.ddp.deferred:
+            raise ValueError("GraphedTrainStep needs FlatDDP(..., deferred=True): collectives run between the two step graphs")
+        self.graph = None        # fwd + bwd (+ optimiser when single-GPU)
+        self.graph_opt = None    # optimiser graph (multi-GPU)
         self.key = None
         self.static = None
         self.out = None
         self.launches_per_step = 0
 
-    def _eager(self, d, metas):
+    def _fwd_bwd(self, d, metas):
         self.opt.zero_grad()
         losses, preds = self.model(d["img"], d["ids"], metas, return_loss=True, text_attention_mask=d["mask"],
                                    gt_bbox=list(d["gt"].unbind(0)), rescale=False)
         losses["loss_total"].backward()
-        if self.ddp is not None:
-            self.ddp.finish()
-        self.opt.step()
         return losses, preds
 
     def _capture(self, img, ids, metas, mask, gt):
         dev = next(self.model.parameters()).device
-        self.static = {"img": torch.empty(img.shape, dtype=torch.float32, device=dev),
+        self.static = {"img": torch.empty(img.shape, dtype=img.dtype if img.dtype == torch.uint8 else torch.float32, device=dev),
                        "ids": torch.empty(ids.shape, dtype=torch.int64, device=dev),
                        "mask": torch.empty(mask.shape, dtype=torch.int64, device=dev),
                        "gt": torch.empty(gt.shape, dtype=gt.dtype, device=dev)}
@@ -49,29 +58,27 @@ class GraphedTrainStep:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(self.warmup):   # real optimiser steps: allocator / workspace / NCCL warm-up before capture
-                self.opt.advance()
-                self._eager(self.static, metas)
-            if self.warmup == 0:
-                # one forward + backward without an optimiser step: fills the model's host-built caches (position
-                # encodings, image-size tensors, attention workspaces, kernel attributes) without touching the parameters
-                self.opt.zero_grad()
-                losses, _ = self.model(self.static["img"], self.static["ids"], metas, return_loss=True,
-                                       text_attention_mask=self.static["mask"], gt_bbox=list(self.static["gt"].unbind(0)))
-                losses["loss_total"].backward()
+            for _ in range(self.warmup):
+                # forward + backward only: fills the model's host-built caches (position encodings, image-size tensors,
+                # attention workspaces, kernel attributes) and warms NCCL without touching parameters or optimiser state
+                losses, _ = self._fwd_bwd(self.static, metas)
                 if self.ddp is not None:
-                    self.ddp.finish()
+                    self.ddp.exchange()
                 del losses
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
         K.reset_launch_count()
-        # With a process group, NCCL's watchdog thread polls CUDA events while we capture: only this thread's calls may be
-        # policed ("thread_local"), otherwise its cudaEventQuery invalidates the capture.  (Round 1: NCCL capture is still
-        # experimental — bench.py keeps N > 1 on eager launches unless --graph-ddp is given.)
+        self.graph = torch.cuda.CUDAGraph()
+        # a process group's watchdog thread may touch CUDA while we capture: police this thread's calls only
         mode = "thread_local" if self.ddp is not None else "global"
         with torch.cuda.graph(self.graph, stream=side, capture_error_mode=mode):   # same stream as the warm-up: autograd's AccumulateGrad nodes stay on it
-            losses, preds = self._eager(self.static, metas)
+            losses, preds = self._fwd_bwd(self.static, metas)
+            if self.ddp is None:
+                self.opt.step()
+        if self.ddp is not None:
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, stream=side, capture_error_mode=mode, pool=self.graph.pool()):
+                self.opt.step()
         self.launches_per_step = K.launch_count()
         self.out = (losses, preds)
 
@@ -84,7 +91,7 @@ class GraphedTrainStep:
     def __call__(self, img, ref_expr_inds, img_metas, text_attention_mask, gt_boxes):
         if not self.model.training:
             raise RuntimeError("GraphedTrainStep captures a training step: call model.train() first")
-        key = (tuple(img.shape), tuple(ref_expr_inds.shape), tuple(tuple(m["img_shape"][:2]) for m in img_metas))
+        key = (tuple(img.shape), img.dtype, tuple(ref_expr_inds.shape), tuple(tuple(m["img_shape"][:2]) for m in img_metas))
         if self.graph is None or key != self.key:
             self.key = key
             self._capture(img, ref_expr_inds, img_metas, text_attention_mask, gt_boxes)
@@ -93,4 +100,7 @@ class GraphedTrainStep:
             self._upload(img, ref_expr_inds, text_attention_mask, gt_boxes)
         self.opt.advance()
         self.graph.replay()
+        if self.ddp is not None:
+            self.ddp.exchange()
+            self.graph_opt.replay()
         return self.out

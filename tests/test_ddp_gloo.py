@@ -56,6 +56,86 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+class _ToyEnc(torch.nn.Module):
+    """The part of BEIT3's surface FlatDDP uses: a flat buffer with a `text_embed` table and the compact-gradient mailbox."""
+
+    def __init__(self):
+        super().__init__()
+        self.table = torch.nn.Embedding(50, 8)
+        self.lin = torch.nn.Linear(8, 8)
+        self._flat = None
+        self._ddp = None
+        self.sparse_text_grad = {"defer": False, "ids": None, "rows": None}
+
+    def flat(self):
+        from simvg_b200.flat import FlatBuffer
+        if self._flat is None:
+            self._flat = FlatBuffer([("w", self.lin.weight), ("text_embed", self.table.weight), ("b", self.lin.bias)])
+        return self._flat.ensure()
+
+
+class _ToyDet(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.vis_enc = _ToyEnc()
+        self.head = torch.nn.Linear(8, 1)
+
+
+class _Opt2:
+    def __init__(self, model):
+        from simvg_b200.flat import FlatBuffer
+        from simvg_b200.optim import _Segment
+        self.segments = [_Segment("vis_enc", model.vis_enc.flat(), 0),
+                         _Segment("rest", FlatBuffer(list(model.head.named_parameters())), 2)]
+        for s_ in self.segments:
+            s_.fb.attach_grads()
+
+
+def _worker_sparse(rank, world, port, out, deferred):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from simvg_b200.optim import FlatDDP
+    torch.manual_seed(0)
+    model = _ToyDet()
+    opt = _Opt2(model)
+    ddp = FlatDDP(model, opt, deferred=deferred)
+    assert model.vis_enc.sparse_text_grad["defer"]
+    g = torch.Generator().manual_seed(100 + rank)
+    ids = torch.randint(0, 50, (6,), generator=g)
+    ids[0] = ids[1]                                           # a repeated id inside one rank
+    rows = torch.randn(6, 8, generator=g)
+    fb = model.vis_enc.flat()
+    dense_local = torch.zeros(50, 8).index_add_(0, ids, rows)  # what a dense backward would have produced on this rank
+    fb.grad_of(0).copy_(torch.randn(8, 8, generator=g))
+    fb.grad_of(2).copy_(torch.randn(8, generator=g))
+    opt.segments[1].fb.grad.copy_(torch.randn(opt.segments[1].fb.numel, generator=g))
+    local = [s_.fb.grad.clone() for s_ in opt.segments]
+    local[0][fb.offsets[1]:fb.offsets[1] + 400] = dense_local.flatten()
+    # the compact form the encoder backward leaves behind; the dense table gradient stays zero
+    model.vis_enc.sparse_text_grad.update(ids=ids, rows=rows)
+    if not deferred:
+        ddp.on_encoder_backward_start()
+        ddp.on_encoder_range_done(0, fb.numel)
+    ddp.finish()
+    torch.save({"local": local, "avg": [s_.fb.grad.clone() for s_ in opt.segments]}, os.path.join(out, "s%d_%d.pt" % (int(deferred), rank)))
+    dist.destroy_process_group()
+
+
+def test_sparse_text_embedding_exchange_world2_gloo(tmp_path):
+    """The text-embedding gradient travels as (ids, rows) per rank (all-gather + local scatter-add) while every other range is
+    all-reduced; both FlatDDP modes (overlap hooks / deferred exchange between the step graphs) must leave each rank with
+    exactly the mean of the dense per-rank gradients."""
+    for deferred in (False, True):
+        port = _free_port()
+        mp.spawn(_worker_sparse, args=(2, port, str(tmp_path), deferred), nprocs=2, join=True)
+        r0 = torch.load(tmp_path / ("s%d_0.pt" % int(deferred)))
+        r1 = torch.load(tmp_path / ("s%d_1.pt" % int(deferred)))
+        for k in range(2):
+            want = (r0["local"][k] + r1["local"][k]) / 2
+            assert torch.allclose(r0["avg"][k], want, atol=1e-6), (deferred, k)
+            assert torch.equal(r0["avg"][k], r1["avg"][k])
+
+
 def test_flat_ddp_world2_gloo(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)

@@ -128,7 +128,7 @@ def test_training_reduces_loss_and_droppath_runs(lib):
         hist.append(float(losses["loss_total"]))
     assert all(h == h for h in hist) and min(hist[-3:]) < hist[0], hist
     sd = opt.state_dict()
-    assert len(sd["param_groups"]) == 2 and sd["param_groups"][0]["lr"] == 2e-5
+    assert len(sd["param_groups"]) == 3 and sd["param_groups"][0]["lr"] == 2e-5 and sd["param_groups"][2]["lr"] == 2e-4
 
 
 def test_graphed_train_step_matches_eager(lib):
@@ -163,7 +163,7 @@ def test_graphed_train_step_matches_eager(lib):
         o1.step()
         eager.append(float(losses["loss_total"]))
     m2, o2 = make()
-    step = GraphedTrainStep(m2, o2, warmup=0)
+    step = GraphedTrainStep(m2, o2, warmup=1)
     graphed = []
     for it in range(5):
         b = batches[it % 2]

@@ -1,0 +1,221 @@
+"""-m gpu: round-2 components — fused optimiser as a torch.optim.Optimizer (groups, frozen layers, EMA), the uint8 input path,
+and the 2-GPU gradient-exchange equivalence (NCCL; skipped with fewer than two devices)."""
+import copy
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _small_model(seed=0, S=128, P=32, freeze_layer=-1, drop_path_rate=0.0):
+    from simvg_b200.models import build_model
+    from tools.synth import model_cfg
+    cfg = model_cfg("base", S, P, drop_path_rate=drop_path_rate)
+    cfg["vis_enc"]["freeze_layer"] = freeze_layer
+    torch.manual_seed(seed)
+    return build_model(cfg)
+
+
+def _step_loss(model, b):
+    losses, _ = model(b["img"], b["ref_expr_inds"], b["img_metas"], return_loss=True,
+                      text_attention_mask=b["text_attention_mask"], gt_bbox=b["gt_bbox"])
+    return losses["loss_total"]
+
+
+def test_fused_optimizer_tracks_torch_adam_on_the_real_model(lib):
+    """Three fused steps (clip 0.15 + Adam-amsgrad over the reference's three lr groups + EMA) against
+    clip_grad_norm_ + torch.optim.Adam(amsgrad=True) + the reference's EMA arithmetic fed the SAME gradients."""
+    from simvg_b200.optim import FusedAdamAMSGrad
+    from tools.synth import make_batch
+    model = _small_model().cuda().eval()
+    twin = copy.deepcopy(model)
+    opt = FusedAdamAMSGrad(model, lr=5e-4, lr_vis_enc=5e-5, lr_lan_enc=5e-5, grad_norm_clip=0.15, ema_alpha=0.999)
+    named = list(twin.named_parameters())
+    ref = torch.optim.Adam([{"params": [p for n, p in named if "vis_enc" in n], "lr": 5e-5},
+                            {"params": [p for n, p in named if "lan_enc" in n], "lr": 5e-5},
+                            {"params": [p for n, p in named if "vis_enc" not in n and "lan_enc" not in n], "lr": 5e-4}],
+                           betas=(0.9, 0.98), eps=1e-9, weight_decay=0, amsgrad=True)
+    shadow = {n: p.detach().clone() for n, p in named}
+    b = make_batch(4, 128, seed=3, device=DEV)
+    for t in range(3):
+        opt.zero_grad()
+        _step_loss(model, b).backward()
+        for (n, p), (_, q) in zip(model.named_parameters(), named):
+            q.grad = p.grad.detach().clone()
+        opt.step()
+        torch.nn.utils.clip_grad_norm_([q for _, q in named], 0.15)
+        ref.step()
+        decay = min(0.999, (t + 1.0) / (t + 10.0))                         # models/utils.py:149
+        for n, q in named:
+            shadow[n].copy_(decay * shadow[n] + (1 - decay) * q.detach())
+    worst = max(float((p.detach() - q.detach()).abs().max()) for (_, p), (_, q) in zip(model.named_parameters(), named))
+    assert worst < 5e-6, worst
+    worst_ema = max(float((opt.ema_view(p) - shadow[n]).abs().max()) for n, p in model.named_parameters())
+    assert worst_ema < 5e-6, worst_ema
+    # checkpoint round trip through torch's own format on the device
+    sd = opt.state_dict()
+    assert len(sd["param_groups"]) == 3 and sd["param_groups"][0]["lr"] == 5e-5 and len(sd["param_groups"][1]["params"]) == 0
+    ref_sd = ref.state_dict()
+    k = max(sd["state"])
+    assert torch.allclose(sd["state"][k]["exp_avg"], ref_sd["state"][k]["exp_avg"], atol=1e-7)
+    assert float(sd["state"][k]["step"]) == 3.0
+
+
+def test_foreign_zero_grad_does_not_lose_gradients(lib):
+    """model.zero_grad() (set_to_none) replaces p.grad by fresh tensors outside the flat buffers: step() must pick them up."""
+    from simvg_b200.optim import FusedAdamAMSGrad
+    from tools.synth import make_batch
+    model = _small_model().cuda().eval()
+    opt = FusedAdamAMSGrad(model, lr=5e-4, lr_vis_enc=5e-5)
+    b = make_batch(2, 128, seed=4, device=DEV)
+    model.zero_grad(set_to_none=True)
+    before = model.head.class_embed_decoder.weight.detach().clone()
+    _step_loss(model, b).backward()
+    opt.step()
+    assert float((model.head.class_embed_decoder.weight.detach() - before).abs().max()) > 0
+    seg = [s for s in opt.segments if s.name == "rest"][0]
+    p = model.head.class_embed_decoder.weight
+    assert p.grad.data_ptr() == seg.fb.grad_of(seg.fb.index(p)).data_ptr()
+
+
+def test_frozen_layers_are_not_updated(lib):
+    from simvg_b200.optim import FusedAdamAMSGrad
+    from tools.synth import make_batch
+    model = _small_model(freeze_layer=2).cuda().train()
+    opt = FusedAdamAMSGrad(model, lr=5e-4, lr_vis_enc=5e-5, grad_norm_clip=0.15, weight_decay=0.01)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    b = make_batch(2, 128, seed=5, device=DEV)
+    for _ in range(2):
+        opt.zero_grad()
+        _step_loss(model, b).backward()
+        opt.step()
+    for n, p in model.named_parameters():
+        moved = float((p.detach() - before[n]).abs().max()) > 0
+        if not p.requires_grad:
+            assert not moved, n                                         # no update, no weight decay
+            assert p.grad is None or float(p.grad.abs().max()) == 0, n
+        elif "mask_token" not in n:
+            assert moved, n
+
+
+def test_uint8_input_path_equals_host_normalisation(lib):
+    """uint8 HWC image -> (normalise + transpose + im2col) fused on the device == mmcv.imnormalize on the host followed by the
+    float NCHW path (pipelines/transforms.py:126-155): identical patch matrix, hence identical losses."""
+    from simvg_b200 import kernels as K
+    from tools.synth import make_batch
+    B, S, P = 3, 128, 32
+    g = torch.Generator().manual_seed(6)
+    u8 = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8)
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    rgb = u8.flip(-1).float()                                             # to_rgb: BGR -> RGB
+    inv = torch.tensor([float(1.0 / s) for s in std], dtype=torch.float64).float()
+    host = ((rgb - torch.tensor(mean)) * inv).permute(0, 3, 1, 2).contiguous()
+    cols_ref = K.im2col_patch(host.cuda(), P)
+    cols = K.im2col_patch_u8(u8.cuda(), P, mean, std, True)
+    assert torch.equal(cols, cols_ref)
+    cols_bgr = K.im2col_patch_u8(u8.cuda(), P, mean, std, False)
+    host_bgr = ((u8.float() - torch.tensor(mean)) * inv).permute(0, 3, 1, 2).contiguous()
+    assert torch.equal(cols_bgr, K.im2col_patch(host_bgr.cuda(), P))
+    model = _small_model().cuda().eval()
+    b = make_batch(B, S, seed=7, device=DEV)
+    b_f = dict(b, img=host.cuda())
+    b_u = dict(b, img=u8.cuda())
+    lf, lu = _step_loss(model, b_f), _step_loss(model, b_u)
+    assert float(lf) == float(lu)
+    lu.backward()
+    assert float(model.vis_enc.beit3.vision_embed.proj.weight.grad.abs().sum()) > 0
+
+
+# ------------------------------------------------------------------------------------------------ two GPUs
+def _ddp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from simvg_b200.optim import FlatDDP, FusedAdamAMSGrad
+    from simvg_b200.runtime import GraphedTrainStep
+    from tools.synth import make_batch
+    res = {}
+    batches = [make_batch(3, 128, seed=50 + 10 * i + rank, device="cuda") for i in range(2)]
+
+    def fresh():
+        m = _small_model(seed=11).cuda().train()
+        for mod in m.modules():           # stochastic layers off: runs must be comparable
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+            if isinstance(mod, torch.nn.MultiheadAttention):
+                mod.dropout = 0.0
+            if hasattr(mod, "attn_drop") and isinstance(mod.attn_drop, float):
+                mod.attn_drop = 0.0
+        return m, FusedAdamAMSGrad(m, lr=2e-4, lr_vis_enc=2e-5, grad_norm_clip=0.15)
+
+    # (1) local gradients without any exchange
+    m0, o0 = fresh()
+    o0.zero_grad()
+    _step_loss(m0, batches[0]).backward()
+    local = [s.fb.grad.clone() for s in o0.segments]
+    gathered = [[torch.empty_like(g) for _ in range(world)] for g in local]
+    for g, lst in zip(local, gathered):
+        dist.all_gather(lst, g)
+    want = [torch.stack(lst).mean(0) for lst in gathered]
+    # (2) overlap mode: ranges reduced from inside the encoder backward (+ sparse text-embedding rows)
+    m1, o1 = fresh()
+    d1 = FlatDDP(m1, o1)
+    d1.broadcast_parameters()
+    o1.zero_grad()
+    _step_loss(m1, batches[0]).backward()
+    d1.finish()
+    torch.cuda.synchronize()
+    res["overlap_err"] = max(float((s.fb.grad - w).abs().max() / w.abs().max()) for s, w in zip(o1.segments, want))
+    chk = [torch.empty_like(o1.segments[0].fb.grad) for _ in range(world)]
+    dist.all_gather(chk, o1.segments[0].fb.grad)
+    res["ranks_identical"] = bool(torch.equal(chk[0], chk[1]))
+    o1.step()
+    # (3) deferred mode under the two-graph runtime: same parameters after two steps as the eager overlap loop
+    o1.zero_grad()
+    _step_loss(m1, batches[1]).backward()
+    d1.finish()
+    o1.step()
+    m2, o2 = fresh()
+    d2 = FlatDDP(m2, o2, deferred=True)
+    d2.broadcast_parameters()
+    step = GraphedTrainStep(m2, o2, d2, warmup=1)
+    for i in range(2):
+        bb = batches[i]
+        step(bb["img"], bb["ref_expr_inds"], bb["img_metas"], bb["text_attention_mask"], torch.stack(bb["gt_bbox"]))
+    torch.cuda.synchronize()
+    keep = [(p, q) for (n, p), (_, q) in zip(m1.named_parameters(), m2.named_parameters())
+            if "k_proj" not in n and "in_proj_bias" not in n]       # zero-gradient key biases random-walk under Adam
+    a = torch.cat([p.detach().flatten() for p, _ in keep])
+    c = torch.cat([q.detach().flatten() for _, q in keep])
+    res["graph_vs_eager_rel"] = float((a - c).norm() / a.norm())
+    res["graphs"] = step.graph_opt is not None
+    torch.save(res, os.path.join(out, "ddp%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
+def test_two_gpu_gradient_exchange_equivalence(lib, tmp_path):
+    """After FlatDDP.finish() every rank's flat gradient equals the mean of the per-rank gradients computed without DDP
+    (the reference's MMDistributedDataParallel semantics, tools/train.py:102-103), bit-identical across ranks; and the
+    two-graph deferred runtime lands on the same parameters as the eager overlapped loop."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        res = torch.load(tmp_path / ("ddp%d.pt" % r))
+        assert res["overlap_err"] < 1e-4, res
+        assert res["ranks_identical"], res
+        assert res["graphs"] and res["graph_vs_eager_rel"] < 2e-3, res

@@ -16,7 +16,7 @@ def test_cabi_exports_every_declared_symbol(lib):
     assert {"simvgb_gemm", "simvgb_attn_fwd", "simvgb_attn_bwd", "simvgb_ln_fwd", "simvgb_ln_bwd", "simvgb_adam_amsgrad"} <= names
     for n in sorted(names):
         assert hasattr(lib, n), "libsimvg_b200.so does not export %s" % n
-    assert lib.simvgb_version() == 100
+    assert lib.simvgb_version() == 200
 
 
 def test_cabi_argument_validation_without_gpu(lib):

@@ -1,0 +1,115 @@
+"""CPU checks of FusedAdamAMSGrad's host side (no kernel launches): it is a torch.optim.Optimizer whose param_groups are the
+reference's own three groups (/root/reference/tools/train.py:78-93), the reference's schedulers drive it, and its checkpoints
+are interchangeable with torch.optim.Adam(amsgrad=True)'s — the optimiser the reference builds (core/optimizer.py:52-68)."""
+import copy
+
+import pytest
+import torch
+
+
+def _model(freeze_layer=-1):
+    from simvg_b200.models import build_model
+    from tools.synth import model_cfg
+    cfg = model_cfg("base", 64, 32)
+    cfg["vis_enc"]["freeze_layer"] = freeze_layer
+    torch.manual_seed(0)
+    return build_model(cfg)
+
+
+def _reference_groups(model, lr, lr_vis, lr_lan):
+    named = list(model.named_parameters())
+    return [{"params": [p for n, p in named if "vis_enc" in n and p.requires_grad], "lr": lr_vis},
+            {"params": [p for n, p in named if "lan_enc" in n and p.requires_grad], "lr": lr_lan},
+            {"params": [p for n, p in named if "lan_enc" not in n and "vis_enc" not in n and p.requires_grad], "lr": lr}]
+
+
+def test_is_torch_optimizer_with_reference_groups_and_schedulers():
+    from simvg_b200.optim import FusedAdamAMSGrad
+    model = _model()
+    opt = FusedAdamAMSGrad(model, lr=5e-4, lr_vis_enc=5e-5, lr_lan_enc=5e-5, grad_norm_clip=0.15)
+    assert isinstance(opt, torch.optim.Optimizer)
+    ref = _reference_groups(model, 5e-4, 5e-5, 5e-5)
+    assert len(opt.param_groups) == 3
+    for g, r in zip(opt.param_groups, ref):
+        assert g["lr"] == r["lr"] and len(g["params"]) == len(r["params"])
+        assert all(a is b for a, b in zip(g["params"], r["params"]))     # same parameters, named_parameters() order
+    assert len(opt.param_groups[1]["params"]) == 0                        # no lan_enc in any SimVG config
+    # the reference's MultiStepLRWarmUp is a LambdaLR over the optimiser (core/scheduler.py); torch raises TypeError for
+    # anything that is not an Optimizer
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda e: 0.1 if e >= 2 else 1.0)
+    for _ in range(2):
+        sched.step()
+    assert opt.param_groups[0]["lr"] == pytest.approx(5e-6) and opt.param_groups[2]["lr"] == pytest.approx(5e-5)
+    seg_lr = {s.name: opt._lr(s) for s in opt.segments}
+    assert seg_lr["vis_enc"] == pytest.approx(5e-6) and seg_lr["rest"] == pytest.approx(5e-5)   # launches read the group's lr
+    torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=10)
+
+
+def test_checkpoint_interchange_with_torch_adam():
+    from simvg_b200.optim import FusedAdamAMSGrad
+    model = _model()
+    twin = copy.deepcopy(model)
+    ref = torch.optim.Adam(_reference_groups(twin, 5e-4, 5e-5, 5e-5), betas=(0.9, 0.98), eps=1e-9, weight_decay=0, amsgrad=True)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(2):
+        for p in twin.parameters():
+            p.grad = torch.randn(p.shape, generator=g) * 1e-2
+        ref.step()
+    sd = ref.state_dict()
+    opt = FusedAdamAMSGrad(model, lr=1.0, lr_vis_enc=1.0, lr_lan_enc=1.0)
+    opt.load_state_dict(copy.deepcopy(sd))
+    assert opt.t == 2 and opt.param_groups[0]["lr"] == 5e-5 and opt.param_groups[2]["lr"] == 5e-4
+    # every moment landed in the flat buffers under the right parameter (q/k/v are adjacent but in a different order there)
+    names = dict((id(p), n) for n, p in model.named_parameters())
+    twin_by_name = dict(twin.named_parameters())
+    checked = 0
+    for grp in opt.param_groups:
+        for p in grp["params"]:
+            seg, i = opt._where[id(p)]
+            st = ref.state[twin_by_name[names[id(p)]]]
+            assert torch.equal(seg.fb.view(i, seg.m), st["exp_avg"]), names[id(p)]
+            assert torch.equal(seg.fb.view(i, seg.v), st["exp_avg_sq"])
+            assert torch.equal(seg.fb.view(i, seg.vmax), st["max_exp_avg_sq"])
+            checked += 1
+    assert checked > 300
+    # and back: our state_dict loads into a fresh torch Adam built the reference way
+    out = opt.state_dict()
+    assert [len(g_["params"]) for g_ in out["param_groups"]] == [len(g_["params"]) for g_ in sd["param_groups"]]
+    ref2 = torch.optim.Adam(_reference_groups(copy.deepcopy(model), 1.0, 1.0, 1.0), betas=(0.9, 0.98), eps=1e-9, amsgrad=True)
+    ref2.load_state_dict(out)
+    k = sorted(sd["state"])[7]
+    assert torch.equal(ref2.state_dict()["state"][k]["exp_avg"], sd["state"][k]["exp_avg"])
+    assert float(ref2.state_dict()["state"][k]["step"]) == 2.0
+    # a checkpoint with a different group layout is refused instead of being zipped silently
+    bad = copy.deepcopy(sd)
+    bad["param_groups"] = bad["param_groups"][:2]
+    with pytest.raises(ValueError):
+        opt.load_state_dict(bad)
+
+
+def test_frozen_layers_are_left_out_of_groups_and_update_ranges():
+    from simvg_b200.optim import FusedAdamAMSGrad
+    model = _model(freeze_layer=2)
+    opt = FusedAdamAMSGrad(model, lr=5e-4, lr_vis_enc=5e-5)
+    frozen = [p for p in model.parameters() if not p.requires_grad]
+    assert len(frozen) == 2 * 40                                          # two layers x (A, B) x 20 tensors
+    in_groups = {id(p) for g in opt.param_groups for p in g["params"]}
+    assert not any(id(p) in in_groups for p in frozen)
+    seg = opt.segments[0]
+    fb = seg.fb
+    covered = torch.zeros(fb.numel, dtype=torch.bool)
+    for lo, hi in seg.ranges():
+        covered[lo:hi] = True
+    for i, p in enumerate(fb.params):
+        assert bool(covered[fb.offsets[i]:fb.offsets[i] + p.numel()].all()) == p.requires_grad, fb.names[i]
+    assert len(seg.ranges()) == 2                                         # embeddings + final LN | layers 2..11
+
+
+def test_ema_decay_schedule_and_views():
+    from simvg_b200.optim import FusedAdamAMSGrad
+    model = _model()
+    opt = FusedAdamAMSGrad(model, lr=5e-4, ema_alpha=0.999)
+    assert [opt.ema_decay(t) for t in (0, 1, 90)] == [0.1, 2.0 / 11.0, 91.0 / 100.0]     # min(alpha, (1+t)/(10+t)): models/utils.py:149
+    assert opt.ema_decay(100000) == 0.999
+    p = model.head.query_embed.weight
+    assert torch.equal(opt.ema_view(p), p.detach()) and opt.ema_view(p).data_ptr() != p.data_ptr()
