@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — images/sec of SimVG's full train step (fwd + DWBD losses + bwd + grad all-reduce + clip + Adam-amsgrad).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg4|cfg5|ref32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu] [--config cfg2|cfg3|cfg4|cfg5|ref32]
 
 Workload (BASELINE.json configs[1], the one `metric` is quoted on): ViT-B/16 BEiT-3 encoder + 6-layer object-token decoder
 (as BASELINE.json names it — the head's constructor default, tgqs_kd_detr_head.py:24-48; the reference's shipped RefCOCO
@@ -10,11 +10,15 @@ One "step" = one optimiser step on one batch.
 
   value  : whole-job img/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e    : the same metric through the public plugin API with HOST (pinned) inputs: every step copies its inputs
-           host->device (prefetched on a copy stream) and reads the loss back device->host
+           host->device (prefetched on a copy stream) and reads the loss back device->host.  Default e2e input = the image as
+           the dataset pipeline holds it before `Normalize` (uint8 HWC; normalise + transpose run fused in the patch-embed
+           prologue on the GPU: 1 byte / sample over PCIe); `e2e_fp32` = the reference's collated float NCHW input.
   roofline: dominant kernel family (by summed device time inside a profiled step): algorithmic FLOPs / CUDA-event time
   cpu_baseline: the CPU oracle (oracle/simvg_oracle.py, kind "port") timed on this host on a bounded sample
   --impl reference: the reference's CPU-eager path (the same oracle port; the reference itself cannot be imported on the
            GPU box — its third-party deps are absent) on all host threads, same metric/config.
+  --impl reference-gpu: the same oracle (plain eager fp32 PyTorch, allow_tf32=False) on cuda:0 at the largest batch that
+           fits — BASELINE.md §4's "reference on GPU" baseline, the one that says something about kernel quality.
 """
 import argparse
 import json
@@ -26,6 +30,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+TRAFFIC_ATTN_CFG2 = None   # filled from the round-2 ncu capture (profiles/r02_attention_ncu.md)
 
 CONFIGS = {
     #        vit      img  patch  bs  dec_layers branch_loss_weight
@@ -149,6 +155,74 @@ def run_reference(args, cfg_name):
     return 0
 
 
+def run_reference_gpu(args, cfg_name):
+    """The oracle (the reference's eager fp32 op sequence) on ONE B200, TF32 off, largest batch that fits (halved on OOM)."""
+    import copy
+
+    import torch
+
+    from oracle import simvg_oracle as O
+    from simvg_b200.models import build_model
+    from tools.synth import make_batch, model_cfg
+    if int(os.environ.get("RANK", 0)) != 0:
+        return 0
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    vit, S, P, bs, dec, blw = CONFIGS[cfg_name]
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.manual_seed(6666)
+    mcfg = model_cfg(vit, S, P, num_decoder_layers=dec, branch_loss_weight=blw)
+    model = build_model(mcfg)
+    sd = {k: v.detach().clone().float().to(dev).requires_grad_(v.dtype.is_floating_point and "empty_weight" not in k)
+          for k, v in model.state_dict().items()}
+    del model
+    params = [v for v in sd.values() if v.requires_grad]
+    vis = [v for k, v in sd.items() if v.requires_grad and "vis_enc" in k]
+    rest = [v for k, v in sd.items() if v.requires_grad and "vis_enc" not in k]
+    opt = torch.optim.Adam([{"params": vis, "lr": 5e-5}, {"params": rest, "lr": 5e-4}], betas=(0.9, 0.98), eps=1e-9,
+                           weight_decay=0, amsgrad=True)
+    om = O.OracleModel(sd, vit, S, P, mcfg["head"])
+    use_bs = args.batch or bs
+    while True:
+        try:
+            batch = make_batch(use_bs, S, seed=6666, device=dev)
+
+            def step():
+                losses, _, _ = om.forward_train(batch["img"], batch["ref_expr_inds"], copy.deepcopy(batch["img_metas"]),
+                                                batch["text_attention_mask"], batch["gt_bbox"])
+                opt.zero_grad()
+                losses["loss_total"].backward()
+                torch.nn.utils.clip_grad_norm_(params, 0.15)
+                opt.step()
+
+            for _ in range(max(args.warmup, 1)):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            break
+        except torch.cuda.OutOfMemoryError:
+            opt.zero_grad(set_to_none=True)
+            torch.cuda.empty_cache()
+            use_bs //= 2
+            if use_bs < 1:
+                raise
+    ms = e0.elapsed_time(e1) / args.steps
+    ips = use_bs / (ms * 1e-3)
+    gf = step_gflops_per_image(vit, S, P, dec)
+    print(json.dumps({
+        "impl": "reference-gpu", "metric": "images/sec (train step, %dpx, bs=%d/GPU)" % (S, bs), "value": ips, "unit": "img/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "dtype": "f32", "data": "synthetic", "batch_used": use_bs,
+        "config": {"workload": "%s: oracle (reference op sequence, eager fp32 PyTorch, TF32 off) on one B200, bs=%d" % (cfg_name, use_bs)},
+        "step_tflops": ips * gf / 1e3}))
+    return 0
+
+
 def cpu_baseline_sample(cfg_name, budget_bs=1, iters=1):
     """Rank-0 bounded CPU sample of the same workload via the oracle (10-30 s)."""
     import copy
@@ -218,7 +292,8 @@ def run_ours(args, cfg_name):
     model = build_model(mcfg).to(dev)
     model.train()
     opt = FusedAdamAMSGrad(model, lr=5e-4, lr_vis_enc=5e-5, betas=(0.9, 0.98), eps=1e-9, weight_decay=0.0, grad_norm_clip=0.15)
-    ddp = FlatDDP(model, opt)
+    use_graph = not args.no_graph
+    ddp = FlatDDP(model, opt, deferred=use_graph)   # graph runtime: collectives run between the two step graphs
     ddp.broadcast_parameters()
 
     # host batches (pinned) — two alternating synthetic batches, data seed = 6666 + rank
@@ -229,13 +304,20 @@ def run_ours(args, cfg_name):
         b["ref_expr_inds"] = b["ref_expr_inds"].pin_memory()
         b["text_attention_mask"] = b["text_attention_mask"].pin_memory()
         b["gt_box_t"] = torch.stack(b["gt_bbox"]).pin_memory()
+        # the same batch as the dataset pipeline holds it before Normalize: uint8 HWC (cv2 channel order)
+        b["img_u8"] = torch.randint(0, 256, (bs, S, S, 3), dtype=torch.uint8,
+                                    generator=torch.Generator().manual_seed(6666 + rank + 1000 * i)).pin_memory()
         host.append(b)
-    h2d_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in ("img", "ref_expr_inds", "text_attention_mask", "gt_box_t"))
+
+    def batch_bytes(img_key):
+        return sum(host[0][k].numel() * host[0][k].element_size() for k in (img_key, "ref_expr_inds", "text_attention_mask", "gt_box_t"))
+
     copy_stream = torch.cuda.Stream()
 
-    def upload(b):
+    def upload(b, img_key="img"):
         with torch.cuda.stream(copy_stream):
-            d = {k: b[k].to(dev, non_blocking=True) for k in ("img", "ref_expr_inds", "text_attention_mask", "gt_box_t")}
+            d = {k: b[k].to(dev, non_blocking=True) for k in ("ref_expr_inds", "text_attention_mask", "gt_box_t")}
+            d["img"] = b[img_key].to(dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return d, ev
@@ -257,19 +339,19 @@ def run_ours(args, cfg_name):
 
     # Whole-step CUDA graph (simvg_b200/runtime.py): the public train-step entry point; --no-graph times the eager loop.
     gstep = None
-    # world > 1: eager launches.  Capturing the NCCL gradient all-reduces inside the step graph hung at N=2 in round 1
-    # (gpurun_out/s2_bench_n2.err) and is left for the next round; the data-parallel path itself is unchanged.
-    if not args.no_graph and (world == 1 or args.graph_ddp):
+    # Every N replays the same captured launch sequence: one graph at N = 1; at N > 1 [fwd + bwd graph] -> NCCL gradient
+    # exchange -> [clip + Adam graph] (no collective is captured; simvg_b200/runtime.py).
+    if use_graph:
         from simvg_b200.runtime import GraphedTrainStep
-        gstep = GraphedTrainStep(model, opt, ddp if world > 1 else None, warmup=max(args.warmup, 3))
+        gstep = GraphedTrainStep(model, opt, ddp if world > 1 else None, warmup=2)
 
     def graphed_step(d, metas):
         losses, _preds = gstep(d["img"], d["ref_expr_inds"], metas, d["text_attention_mask"], d["gt_box_t"])
         return losses["loss_total"]
 
-    def timed(n, e2e):
+    def timed(n, e2e, img_key="img"):
         """-> ms per step (device time via CUDA events, max over ranks)."""
-        res, ev = upload(host[0])
+        res, ev = upload(host[0], img_key)
         torch.cuda.current_stream().wait_event(ev)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -278,7 +360,7 @@ def run_ours(args, cfg_name):
         for i in range(n):
             cur = res
             if e2e:
-                nxt, ev = upload(host[(i + 1) % 2])      # this step's H2D copy, overlapped on the copy stream
+                nxt, ev = upload(host[(i + 1) % 2], img_key)      # this step's H2D copy, overlapped on the copy stream
             # graph mode: the staged device batch is copied (device->device) into the graph's static inputs, then replayed
             loss = (graphed_step if gstep is not None else train_step)(cur, host[i % 2]["img_metas"])
             if e2e:
@@ -294,15 +376,17 @@ def run_ours(args, cfg_name):
             ms = float(t)
         return ms, loss_host
 
-    # warm-up (also warms the caching allocator; in graph mode the first call captures)
+    # warm-up (also warms the caching allocator; in graph mode the first call of each input kind captures)
     timed(max(args.warmup, 3), e2e=False)
+    timed(max(args.warmup, 3), e2e=True, img_key="img_u8")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     K.reset_launch_count()
     ms, _ = timed(args.steps, e2e=False)
     launches = K.launch_count() if gstep is None else gstep.launches_per_step * args.steps
-    ms_e2e, last_loss = timed(args.steps, e2e=True)
+    ms_e2e, last_loss = timed(args.steps, e2e=True, img_key="img_u8")
+    ms_e2e_f32, _ = timed(args.steps, e2e=True, img_key="img")
     clocks = sampler.stop() if rank == 0 else None
 
     # roofline leg: one profiled EAGER step with CUDA events around every GEMM / attention launch (events cannot bracket
@@ -311,11 +395,23 @@ def run_ours(args, cfg_name):
     torch.cuda.current_stream().wait_event(ev)
     torch.cuda.synchronize()
     if gstep is not None:
-        opt.advance()
+        graphed = True
+        gstep = None                # release the step graphs' memory pool before the eager profiled step (ViT-L bs=64 needs it)
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        opt.graph_mode = False      # the profiled step is eager
+    else:
+        graphed = False
     K.profile_start()
     train_step(res, host[0]["img_metas"])
     prof = K.profile_stop()
     barrier()
+    # attention forward + backward are one kernel family for the "dominant family" pick (bench.py used to split them, which let
+    # the GEMM family win while attention as a whole was the larger share)
+    if "attn_fwd" in prof and "attn_bwd" in prof:
+        a, b2 = prof["attn_fwd"], prof["attn_bwd"]
+        prof["attention"] = (a[0] + b2[0], a[1] + b2[1], a[2] + b2[2])
 
     if rank != 0:
         if world > 1:
@@ -328,16 +424,20 @@ def run_ours(args, cfg_name):
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
-    fam = max(prof, key=lambda k: prof[k][1]) if prof else None
+    fam = max((k for k in prof if k not in ("attn_fwd", "attn_bwd")), key=lambda k: prof[k][1]) if prof else None
     roofline = None
     if fam:
         n, tot_ms, fl = prof[fam]
         ach = fl / (tot_ms * 1e-3) / 1e12
         # DRAM traffic of the family's largest launch from the committed ncu --set full capture (profiles/r01_gemm_ncu.md):
         # QKV forward GEMM pair (vision 102464x2304x768 + text 1280x2304x768): 597.5 MB read+write vs 644.5 MB algorithmic.
-        traffic = 597.5e6 if (fam == "gemm" and cfg_name == "cfg2") else None
+        traffic, note = None, None
+        if cfg_name == "cfg2" and fam == "gemm":
+            traffic, note = 597.5e6, "bytes/launch of the largest launch (QKV fwd GEMM, both experts), ncu capture in profiles/r01_gemm_ncu.md; algorithmic 644.5e6"
+        elif cfg_name == "cfg2" and fam == "attention":
+            traffic, note = TRAFFIC_ATTN_CFG2, "mean DRAM bytes/launch over the family (fwd + bwd incl. delta / dq-convert), ncu captures in profiles/r02_attention_ncu.md"
         roofline = {"bound": "tensor", "kernel": fam, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                    "traffic": traffic, "traffic_note": "bytes/launch of the largest launch (QKV fwd GEMM, both experts), ncu capture in profiles/r01_gemm_ncu.md; algorithmic 644.5e6",
+                    "traffic": traffic, "traffic_note": note,
                     "launches": n, "avg_ms": tot_ms / n, "peak_source": peak_src,
                     "families": {k: {"launches": v[0], "ms": v[1], "tflops": v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None}
                                  for k, v in prof.items()}}
@@ -359,10 +459,16 @@ def run_ours(args, cfg_name):
                    "global_batch": world * bs, "seq_len": (S // P) ** 2 + 21, "parallelism": "dp%d" % world,
                    "l2": "inputs+activations per step (>40 GB) far exceed the 126 MB L2; no explicit flush",
                    "operands": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LN / softmax / optimiser",
-                   "launch": "whole step replayed as one CUDA graph (simvg_b200.runtime.GraphedTrainStep)" if gstep is not None else "eager launches"},
+                   "launch": ("eager launches" if not graphed else
+                              "whole step replayed as one CUDA graph (simvg_b200.runtime.GraphedTrainStep)" if world == 1 else
+                              "two CUDA graphs per step (fwd+bwd | clip+Adam) with the NCCL gradient exchange between them")},
         "clocks": clocks,
-        "e2e": {"value": ips_e2e, "unit": "img/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                "last_loss": last_loss},
+        "e2e": {"value": ips_e2e, "unit": "img/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": batch_bytes("img_u8"),
+                "d2h_bytes_per_step": 4, "last_loss": last_loss,
+                "input": "uint8 HWC image (pre-Normalize), normalise + transpose fused into the patch-embed prologue on the GPU"},
+        "e2e_fp32": {"value": world * bs / (ms_e2e_f32 * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e_f32,
+                     "h2d_bytes_per_step": batch_bytes("img"), "d2h_bytes_per_step": 4,
+                     "input": "float32 NCHW image, normalised on the host (the reference's collated input)"},
         "gpu_launches": launches,
         "step_gflops_per_image": gf,
         "step_tflops": ips * gf / 1e3,   # whole job
@@ -381,17 +487,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--dec-layers", type=int, default=0)
     ap.add_argument("--ref-batch", type=int, default=2, help="images per CPU-reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch loop instead of the whole-step CUDA graph")
-    ap.add_argument("--graph-ddp", action="store_true", help="experimental: also capture the step graph (with its NCCL all-reduces) when N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, args.config)
+    if args.impl == "reference-gpu":
+        return run_reference_gpu(args, args.config)
     return run_ours(args, args.config)
 
 

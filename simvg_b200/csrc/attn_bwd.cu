@@ -16,7 +16,10 @@
 // terms (hi + mid + lo, exact to fp32 rounding) in columns 0-2 of a 32-byte K-slot written by the producer warp.
 //     dV_j += P^T dO_i    (A = P^T  from TMEM)
 //     dK_j += dS^T Q_i    (A = dS^T from TMEM, written in place over dP^T)
-//     dQ_i  = dS K_j      (A = dS^T tile in smem read MN-major, B = K_j MN-major; fp32 red.global.add)
+//     dQ_i  = dS K_j      (A = dS^T tile in smem read MN-major, B = K_j MN-major; the fp32 tile is staged in shared memory and
+//                          added to the global accumulator by ONE bulk tensor reduction per 32-column half
+//                          (cp.reduce.async.bulk.tensor .add.f32): round 1 issued 8192 red.global.add.v4 per tile pair from the
+//                          LSU, 820 of the ~3000 L1 data-pipe wavefronts per pair — the pipe that also feeds the MMA operands)
 // TMEM columns: S^T [0,128)  dP^T/dS^T [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)  P^T (bf16 pairs) [448,512).
 // Tensor-pipe order per pair: S(i+1), dK(i), dP(i+1), dV(i), dQ(i) — in-order execution makes the in-place dS^T -> dP^T
 // hand-over safe without a round trip through the issuing warp.
@@ -52,7 +55,7 @@ constexpr int kComputeThreads = 512;    // four warps per TMEM lane quarter, one
 constexpr int kQS = SIMVGB_BWD_STAGES;   // Q_i / dO_i / LSE_i / delta_i ring depth (TMA latency is ~1.5 us)
 constexpr int kStatSlots = 2 * kQS + 1;                  // 32-byte K-slots: (LSE, delta) per stage + one all-ones A slot
 constexpr int kStatTiles = (kStatSlots + 3) / 4;         // four K-slots per 128B-swizzled [128 x 64] tile
-constexpr int kBwdTiles = 2 + 2 * kQS + 4 + kStatTiles;  // K, V, Q[kQS], dO[kQS], dS^T[2 buffers](2 sub-tiles), statistic slots
+constexpr int kBwdTiles = 2 + 2 * kQS + 4 + kStatTiles;  // K, V, Q[kQS], dO[kQS], dS^T (2 sub-tiles), dQ staging (2 fp32 sub-tiles), statistic slots
 constexpr int kStageBytes = 2 * 2 * kTile * 4;           // raw LSE_i / delta_i rows (bulk-copied, 2 deep), converted into K-slots by warp 0
 // 14 tiles + staging + barriers = 231,680 B of the 232,448 B a CTA may own: no slack for manual alignment, so the dynamic
 // shared-memory window itself must be 1024-byte aligned (it is when the kernel has no static __shared__; checked at entry).
@@ -74,13 +77,22 @@ struct AttnBwdParams {
 
 static long long* g_attn_trace = nullptr;
 
-struct AttnMaps6 {
+struct AttnMaps9 {
   CUtensorMap qkv_full, qkv_tail, qkv_text, do_full, do_tail, do_text;
+  CUtensorMap dq_full, dq_tail, dq_text;   // fp32 dQ accumulators, 32-column boxes (reduction targets)
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// fp32 tile (shared memory, 128B-swizzled box of the tensor map) += into global memory: one TMA reduction, line-granular at L2
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void dq_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four dQ write-back warps
 // 1-D bulk copy global -> shared, completion on an mbarrier (bytes: multiple of 16, both addresses 16-byte aligned)
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -89,7 +101,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 }
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
-attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
+attn_bwd_kernel(const __grid_constant__ AttnMaps9 maps, const AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();         // 128B-swizzled TMA / UMMA tiles need 1024-byte alignment
@@ -97,7 +109,9 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
   uint8_t* sV = smem + kTileBytes;
   uint8_t* sQ = smem + 2 * kTileBytes;                 // [kQS]
   uint8_t* sdO = smem + (2 + kQS) * kTileBytes;        // [kQS]
-  uint8_t* sdS = smem + (2 + 2 * kQS) * kTileBytes;    // [2 buffers][2 sub-tiles]: rows = keys, 128 queries per row
+  uint8_t* sdS = smem + (2 + 2 * kQS) * kTileBytes;    // [2 sub-tiles]: rows = keys, 128 queries per row (single buffer: dQ(i) has
+                                                       // long retired when the compute warps reach the dS^T store of pair i+1)
+  uint8_t* sdQ = smem + (4 + 2 * kQS) * kTileBytes;    // [2 sub-tiles]: 128 query rows x 32 fp32 columns each, 128B-swizzled
   uint8_t* sStat = smem + (6 + 2 * kQS) * kTileBytes;  // K-slot n: rows 128 B apart, 16-byte chunks 2n', 2n'+1 (n' = n % 4) of tile n / 4
   float* sStage = reinterpret_cast<float*>(smem + kBwdTiles * kTileBytes);   // [2][2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdTiles * kTileBytes + kStageBytes);
@@ -109,7 +123,7 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
   uint64_t* s_empty = s_full + 2;          // every compute warp has S^T(i) in registers
   uint64_t* p_full = s_full + 3;           // P^T(i), dS^T(i) (TMEM) and dS^T(i) (smem) written
   uint64_t* pt_free = s_full + 4;          // dV(i) has consumed P^T(i)
-  uint64_t* ds_free = s_full + 5;          // [2]: dQ(i) has consumed smem dS^T buffer i & 1
+  uint64_t* ds_free = s_full + 5;          // [0]: dQ(i) has consumed the smem dS^T tile ([1] unused)
   uint64_t* dq_full = s_full + 7;
   uint64_t* dq_empty = s_full + 8;
   uint64_t* mma_done = s_full + 9;
@@ -268,7 +282,6 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
     issue_dp(0);
     for (int i = 0; i < nq; ++i) {
       const int s = i % kQS;
-      const int pb = i & 1;   // smem dS^T buffer of this pair
       if (trace) p.ts[i * 16 + 0] = clock64();
       if (i + 1 < nq) {       // S^T(i+1) runs on the tensor pipe while the compute warps work on pair i
         mbar_wait(&qdo_full[(i + 1) % kQS], ((i + 1) / kQS) & 1);
@@ -302,7 +315,7 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);
       if (trace) p.ts[i * 16 + 4] = clock64();
       tc_fence_after();
-      const uint64_t dsm = dS_mn0 + pb * 2 * kTileStep;
+      const uint64_t dsm = dS_mn0;
       if (!(SIMVGB_DBG(p) & 16) && elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // dQ_i = dS K_j        (A: smem dS^T tile read MN-major, B: K_j MN-major)
@@ -310,7 +323,7 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       }
       if (elect_one()) {
         umma_commit(dq_full);
-        umma_commit(&ds_free[pb]);
+        umma_commit(&ds_free[0]);
         if (i == nq - 1) umma_commit(mma_done);
       }
       __syncwarp();
@@ -370,8 +383,8 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
         dk[t] = pack_bf16x2(p0 * __uint_as_float(dv[2 * t]), p1 * __uint_as_float(dv[2 * t + 1]));
       }
       tmem_st16(tmdP + lane_base + 32 * c, dk);   // dS^T in place over this thread's own (already loaded) dP^T columns
-      if (i > 1) mbar_wait(&ds_free[i & 1], ((i - 2) >> 1) & 1);   // dQ(i-2) has consumed this smem buffer
-      const uint32_t adS = smem_u32(sdS) + (i & 1) * 2 * kTileBytes;
+      if (i > 0) mbar_wait(&ds_free[0], (i - 1) & 1);   // dQ(i-1) has consumed the smem dS^T tile
+      const uint32_t adS = smem_u32(sdS);
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4)
         st_shared_v4(adS + swz_off(r, c * 4 + q4), dk[4 * q4], dk[4 * q4 + 1], dk[4 * q4 + 2], dk[4 * q4 + 3]);
@@ -405,15 +418,13 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
     }
     tc_fence_before();
   } else {
-    // ------------------------------ dQ write-back (fp32 atomics) and dV ------------------------------
+    // ------------------------------ dQ write-back (bulk tensor reductions) and dV ------------------------------
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+    const bool leader = warp == 18 && lane == 0;
+    const uint32_t stage_row = smem_u32(sdQ) + r * 128;
     for (int i = 0; i < nq; ++i) {
-      const int qv = i * kTile + r;
-      float* dst = nullptr;
-      if (qv < g.Lv) dst = p.dq_acc_v + ((long long)b * g.Lv + qv) * g.D + h * kHeadDim;
-      else if (qv >= g.T0 && qv < g.T0 + g.Lt) dst = p.dq_acc_t + ((long long)b * g.Lt + (qv - g.T0)) * g.D + h * kHeadDim;
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
       uint32_t v0[32], v1[32];
@@ -423,53 +434,37 @@ attn_bwd_kernel(const __grid_constant__ AttnMaps6 maps, const AttnBwdParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_empty);
-      // Lane pairs (2k, 2k+1) swap half of their row so that each red.v4 instruction has the two lanes of a pair writing
-      // adjacent 16-byte chunks of the SAME row: every L2 atomic operation then covers a full 32-byte sector (half as
-      // many L2 atomic operations as one-row-per-lane).  even lane keeps float4 #0,2,4,6 of its row and receives the same
-      // of the odd lane's row; the odd lane keeps / receives float4 #1,3,5,7.
-#if !SIMVGB_BWD_DQ_PAIR
-      if (!(SIMVGB_DBG(p) & 1) && dst != nullptr) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          red_add_v4(dst + 4 * q, __uint_as_float(v0[4 * q]), __uint_as_float(v0[4 * q + 1]), __uint_as_float(v0[4 * q + 2]), __uint_as_float(v0[4 * q + 3]));
-          red_add_v4(dst + 32 + 4 * q, __uint_as_float(v1[4 * q]), __uint_as_float(v1[4 * q + 1]), __uint_as_float(v1[4 * q + 2]), __uint_as_float(v1[4 * q + 3]));
-        }
-      }
-#else
       if (!(SIMVGB_DBG(p) & 1)) {
-        const bool odd = lane & 1;
-        const unsigned long long my = reinterpret_cast<unsigned long long>(dst);
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, my, 1);
-        float* row_e = reinterpret_cast<float*>(odd ? other : my);   // row owned by the even lane of the pair
-        float* row_o = reinterpret_cast<float*>(odd ? my : other);   // row owned by the odd lane
-        auto flush_half = [&](const uint32_t (&v)[32], int col0) {
+        if (leader) bulk_wait_read0();      // the previous tile's reductions have finished READING the staging tile
+        dq_sync();
+        // row r of the fp32 tile: 64 columns = two 128-byte rows (one per 32-column sub-tile), 16-byte chunks XOR-swizzled with
+        // the row index exactly as TMA's 128B swizzle expects (conflict-free: 8 consecutive rows cover all 32 banks)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float recv[4], own[4];
+        for (int c = 0; c < 8; ++c) {
+          st_shared_v4(stage_row + ((c ^ (r & 7)) << 4), v0[4 * c], v0[4 * c + 1], v0[4 * c + 2], v0[4 * c + 3]);
+          st_shared_v4(stage_row + kTileBytes + ((c ^ (r & 7)) << 4), v1[4 * c], v1[4 * c + 1], v1[4 * c + 2], v1[4 * c + 3]);
+        }
+        fence_proxy_async();                // generic-proxy stores -> visible to the bulk (async-proxy) reads
+        dq_sync();
+        if (leader) {
+          const bool full = i < g.nfull;
+          const bool tail = (i == g.nfull) && g.tail_rows > 0;
+          const bool text = (i == g.text_tile) && g.Lt > 0;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              // float4 indices 2q (even) and 2q+1 (odd) of this 32-column half: send the one the partner keeps
-              const uint32_t ev = v[4 * (2 * q) + e], ov = v[4 * (2 * q + 1) + e];
-              recv[e] = __uint_as_float(__shfl_xor_sync(0xffffffffu, odd ? ev : ov, 1));
-              own[e] = __uint_as_float(odd ? ov : ev);
-            }
-            const int col = col0 + 4 * (2 * q + (odd ? 1 : 0));
-            // instruction A: the even lane's row; instruction B: the odd lane's row
-            if (row_e != nullptr) {
-              if (odd) red_add_v4(row_e + col, recv[0], recv[1], recv[2], recv[3]);
-              else red_add_v4(row_e + col, own[0], own[1], own[2], own[3]);
-            }
-            if (row_o != nullptr) {
-              if (odd) red_add_v4(row_o + col, own[0], own[1], own[2], own[3]);
-              else red_add_v4(row_o + col, recv[0], recv[1], recv[2], recv[3]);
+          for (int sub = 0; sub < 2; ++sub) {
+            const uint32_t src = smem_u32(sdQ) + sub * kTileBytes;
+            const int col = h * kHeadDim + 32 * sub;
+            if (full) tma_reduce_add_3d(&maps.dq_full, src, col, i * kTile, b);
+            else {
+              if (tail) tma_reduce_add_3d(&maps.dq_tail, src, col, i * kTile, b);
+              if (text) tma_reduce_add_3d(&maps.dq_text, src + g.text_row * 128, col, 0, b);
             }
           }
-        };
-        flush_half(v0, 0);
-        flush_half(v1, 32);
+          bulk_commit();
+        }
       }
-#endif
     }
+    if (leader) bulk_wait_all0();           // shared memory must outlive the last bulk read
     mbar_wait(mma_done, 0);
     tc_fence_after();
     const int kv = kt * kTile + r;
@@ -569,9 +564,26 @@ extern "C" int simvgb_attn_bwd(const simvgb_attn_args* a, void* stream) {
     p.ts = g_attn_trace;      // optional clock64 trace (tools/attn_trace.py)
   }
   const int lse_stride = p.g.ntiles * kTile;
-  AttnMaps6 maps;
+  AttnMaps9 maps;
   if (make_attn_maps(&maps.qkv_full, &maps.qkv_tail, &maps.qkv_text, p.g, a->qkv_v, a->qkv_t, 3 * D)) return -1;
   if (make_attn_maps(&maps.do_full, &maps.do_tail, &maps.do_text, p.g, a->dout_v, a->dout_t, D)) return -1;
+  {   // fp32 accumulators [B*L, D]: dims (D, tokens-per-sample, B), box 32 columns (= one 128-byte swizzle row) x tile rows
+    const AttnGeom& g = p.g;
+    uint64_t dims[3] = {(uint64_t)D, (uint64_t)g.Lv, (uint64_t)g.B};
+    uint64_t strides[2] = {(uint64_t)D * 4, (uint64_t)D * 4 * g.Lv};
+    uint32_t box[3] = {32, kTile, 1};
+    if (make_tmap(&maps.dq_full, a->dq_acc_v, 4, 3, dims, strides, box, 1)) return -1;
+    box[1] = g.tail_rows > 0 ? g.tail_rows : 8;
+    if (make_tmap(&maps.dq_tail, a->dq_acc_v, 4, 3, dims, strides, box, 1)) return -1;
+    if (g.Lt > 0) {
+      dims[1] = g.Lt;
+      strides[1] = (uint64_t)D * 4 * g.Lt;
+      box[1] = g.Ltp;
+      if (make_tmap(&maps.dq_text, a->dq_acc_t, 4, 3, dims, strides, box, 1)) return -1;
+    } else {
+      maps.dq_text = maps.dq_tail;
+    }
+  }
 
   // positions of the virtual axis that belong to neither token range are never written by the delta kernel: keep them 0
   SIMVGB_CUDA(cudaMemsetAsync(a->delta, 0, sizeof(float) * (size_t)a->B * a->H * lse_stride, s));

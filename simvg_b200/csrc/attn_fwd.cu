@@ -20,7 +20,7 @@
 //   * P goes to TMEM as packed bf16 pairs (tcgen05.st) and is the A operand of O += P V (TS-form MMA); V is consumed
 //     MN-major straight from its token-major TMA tile; online softmax with lazy rescaling (O is touched only when a row
 //     maximum grows by more than 2^8).
-// Warp roles: 0 = TMA producer, 1 / 2 = tcgen05.mma issuer of tile A / B, 3-10 = softmax of tile A, 11-18 = softmax of tile B.  TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)  P_A [384,448)  P_B [448,512).
+// Warp roles: 0 = TMA producer, 1 = tcgen05.mma issuer, 2-9 = softmax of tile A, 10-17 = softmax of tile B.  TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)  P_A [384,448)  P_B [448,512).
 #include <stdlib.h>
 
 #include "attn_common.cuh"
@@ -34,7 +34,10 @@ namespace simvgb {
 #ifndef SIMVGB_FWD_KS
 #define SIMVGB_FWD_KS 3
 #endif
-constexpr int kFwdThreads = 608;
+#ifndef SIMVGB_FWD_STAGGER
+#define SIMVGB_FWD_STAGGER 0   // 1: hold tile B's first S product back until tile A is half-way through key tile 0 (anti-phase)
+#endif
+constexpr int kFwdThreads = 576;
 constexpr int kKS = SIMVGB_FWD_KS;   // K ring depth = V ring depth
 constexpr int kFwdSmem = (2 + 2 * kKS) * kTileBytes + 1024 /*align*/ + 512 /*barriers*/ + 4096 /*row-max exchange*/;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -48,7 +51,15 @@ struct AttnFwdParams {
   int npairs;                // ntiles / 2  (work items with two query tiles)
   int n_full_items;          // B * H * npairs
   int n_items;               // + B * H single-tile items when ntiles is odd
+  long long* ts;             // SIMVGB_FWD_TRACE builds only: clock64 trace of CTA 0's first work item (tools/attn_fwd_trace.py)
 };
+
+#ifdef SIMVGB_FWD_TRACE
+static long long* g_fwd_trace = nullptr;
+#define FWD_TS(cond, slot) do { if (cond) p.ts[(slot)] = clock64(); } while (0)
+#else
+#define FWD_TS(cond, slot) do { } while (0)
+#endif
 
 struct FwdItem {
   int b, h, tA, tB;   // tB < 0: only tile A
@@ -122,7 +133,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   uint64_t* p_full = s_full + 4;           // [2]  P_X(j) written (and O_X rescaled if it had to be)
   uint64_t* pv_done = s_full + 6;          // [2]  O_X += P_X(j) V(j) complete
   uint64_t* o_free = s_full + 8;           // [2]  epilogue X holds O_X in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 10);
+  uint64_t* mid = s_full + 10;             // tile A is half-way through the first key tile of a work item (staggers tile B)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 11);
   float* xchg = reinterpret_cast<float*>(smem + (2 + 2 * kKS) * kTileBytes + 512);   // [tile 2][parity 2][half 2][128 rows]
 
   const AttnGeom& g = p.g;
@@ -141,8 +153,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
       mbar_init(&s_full[x], 1); mbar_init(&s_free[x], 8);     // one elected arrival per softmax warp
       mbar_init(&p_full[x], 8); mbar_init(&pv_done[x], 1); mbar_init(&o_free[x], 8);
     }
+    mbar_init(mid, 8);
     for (int s = 0; s < kKS; ++s) {
-      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 2); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 2);   // both issuers release
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
     fence_barrier_init();
   }
@@ -156,7 +169,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (uniform registers for UTCHMMA)
 
-  if (warp < 3) {
+  if (warp < 2) {
     if (warp == 0) {
       // ------------------------------ TMA producer ------------------------------
       if (lane == 0) {
@@ -188,83 +201,100 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
           for (int j = 1; j < nk; ++j) { load_k(j); load_v(j); }
         }
       }
-    } else {
-      // ------------------------------ MMA issuers: warp 1 drives tile A, warp 2 tile B ------------------------------
-      // One issuing warp per query tile: S_X(j+1) goes out the moment softmax X has pulled S_X(j) out of TMEM and P_X(j) V_j the
-      // moment P_X(j) is written, whatever the other tile is doing (a single issuer blocked on one tile's barrier delayed the
-      // other's products).  Warp-uniform control flow, single-lane issue.
-      const int x = warp - 1;
+    } else if (warp == 1) {
+      // ------------------------------ MMA issuer: warp-uniform control flow, single-lane issue ------------------------------
       const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);  // A = P (TMEM), B = V (MN-major)
-      constexpr uint32_t kStep = kTileBytes >> 4;
-      const uint64_t dQ = umma_smem_desc(smem_u32(sQ), 16, 1024) + x * kStep;
+      const uint64_t dQ0 = umma_smem_desc(smem_u32(sQ), 16, 1024);
       const uint64_t dK0 = umma_smem_desc(smem_u32(sK), 16, 1024);
       const uint64_t dV0 = umma_smem_desc(smem_u32(sV), 8192, 1024);
-      const uint32_t tmS = tmem + 128 * x, tmO = tmem + 256 + 64 * x, tmP = tmem + 384 + 64 * x;
-      uint32_t kc = 0, vc = 0, sc = 0, pc = 0, ic = 0;
+      constexpr uint32_t kStep = kTileBytes >> 4;
+      uint32_t kc = 0, vc = 0, mc = 0, sc[2] = {0, 0}, pc[2] = {0, 0}, ic[2] = {0, 0};
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
         const FwdItem w = decode_item(p, it);
-        if (x == 1 && w.tB < 0) {
-          // single-tile item: tile B idles, but every K / V slot still needs this warp's release (the empty barriers count two)
-          for (int j = 0; j < nk; ++j) {
-            mbar_wait(&k_full[kc % kKS], (kc / kKS) & 1);
-            if (lane == 0) mbar_arrive(&k_empty[kc % kKS]);
-            ++kc;
-            mbar_wait(&v_full[vc % kKS], (vc / kKS) & 1);
-            if (lane == 0) mbar_arrive(&v_empty[vc % kKS]);
-            ++vc;
-          }
-          continue;
-        }
-        // S_X = Q_X K_j^T; `last` also releases the Q_X buffer
-        auto issue_s = [&](bool last) {
-          const uint32_t kslot = kc % kKS;
-          mbar_wait(&k_full[kslot], (kc / kKS) & 1);
-          mbar_wait(&s_free[x], (sc & 1) ^ 1);                // softmax X has pulled the previous S_X out of TMEM
+        const bool both = w.tB >= 0;
+        // S_X = Q_X K_j^T into TMEM columns [128 X, 128 X + 128); `last` also releases the Q_X buffer
+        auto issue_s = [&](int x, uint32_t kslot, bool last) {
+          mbar_wait(&s_free[x], (sc[x] & 1) ^ 1);             // softmax X has pulled the previous S_X out of TMEM
           tc_fence_after();
-          const uint64_t dk = dK0 + kslot * kStep;
+          const uint64_t dq = dQ0 + x * kStep, dk = dK0 + kslot * kStep;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kHeadDim / 16; ++k) umma_f16_ss(tmS, dQ + 2 * k, dk + 2 * k, idesc_s, k > 0);
+            for (int k = 0; k < kHeadDim / 16; ++k) umma_f16_ss(tmem + 128 * x, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
             umma_commit(&s_full[x]);
-            umma_commit(&k_empty[kslot]);
             if (last) umma_commit(&q_empty[x]);
           }
           __syncwarp();
-          ++sc;
-          ++kc;
+          ++sc[x];
         };
         // O_X (+)= P_X V_j
-        auto issue_pv = [&](bool first) {
-          const uint32_t vslot = vc % kKS;
-          mbar_wait(&v_full[vslot], (vc / kKS) & 1);
-          mbar_wait(&p_full[x], pc & 1);
-          if (first) mbar_wait(&o_free[x], (ic & 1) ^ 1);     // the previous item's epilogue has read O_X
+        auto issue_pv = [&](int x, uint32_t vslot, bool first) {
+          mbar_wait(&p_full[x], pc[x] & 1);
+          if (first) mbar_wait(&o_free[x], (ic[x] & 1) ^ 1);  // the previous item's epilogue has read O_X
           tc_fence_after();
           const uint64_t dv = dV0 + vslot * kStep;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kTile / 16; ++k)   // A = P[:, 16k .. 16k+16) = 8 packed TMEM columns
-              umma_f16_ts(tmO, tmP + 8 * k, dv + k * 128, idesc_o, (!first || k > 0) ? 1u : 0u);
+              umma_f16_ts(tmem + 256 + 64 * x, tmem + 384 + 64 * x + 8 * k, dv + k * 128, idesc_o, (!first || k > 0) ? 1u : 0u);
             umma_commit(&pv_done[x]);
+          }
+          __syncwarp();
+          ++pc[x];
+        };
+        // SIMVGB_FWD_STAGGER: tile B's first S product is held back until A's softmax is half-way through key tile 0, which keeps
+        // the two tiles in anti-phase for the whole item.  Measured (tools/attn_fwd_trace.py): the anti-phase holds (B lags A by
+        // ~1600 of 3130 clk) and the per-tile period drops 3350 -> 3130 clk, but every item then ends with half a period of tile B
+        // alone: 0.960 ms against 0.841 ms without — off by default.
+        uint32_t kslot0 = kc % kKS;
+        mbar_wait(&q_full[0], ic[0] & 1);
+        mbar_wait(&k_full[kslot0], (kc / kKS) & 1);
+        issue_s(0, kslot0, nk == 1);
+        if (!SIMVGB_FWD_STAGGER && both) {
+          mbar_wait(&q_full[1], ic[1] & 1);
+          issue_s(1, kslot0, nk == 1);
+        }
+        ++kc;
+        for (int j = 0; j < nk; ++j) {
+          const bool more = j + 1 < nk;
+          const uint32_t vslot = vc % kKS;
+          const uint32_t kslot = kc % kKS;
+          if (more) {
+            mbar_wait(&k_full[kslot], (kc / kKS) & 1);
+            issue_s(0, kslot, j + 2 == nk);
+          }
+          if (j == 0) {
+            if (SIMVGB_FWD_STAGGER) {
+              mbar_wait(mid, mc & 1);
+              ++mc;
+            }
+            if (SIMVGB_FWD_STAGGER && both) {
+              mbar_wait(&q_full[1], ic[1] & 1);
+              issue_s(1, kslot0, nk == 1);
+            }
+          }
+          mbar_wait(&v_full[vslot], (vc / kKS) & 1);
+          issue_pv(0, vslot, j == 0);
+          if (both) {
+            if (more) issue_s(1, kslot, j + 2 == nk);
+            issue_pv(1, vslot, j == 0);
+          }
+          if (elect_one()) {
+            if (j == 0) umma_commit(&k_empty[kslot0]);
+            if (more) umma_commit(&k_empty[kslot]);
             umma_commit(&v_empty[vslot]);
           }
           __syncwarp();
-          ++pc;
+          if (more) ++kc;
           ++vc;
-        };
-        mbar_wait(&q_full[x], ic & 1);
-        issue_s(nk == 1);
-        for (int j = 0; j < nk; ++j) {
-          if (j + 1 < nk) issue_s(j + 2 == nk);
-          issue_pv(j == 0);
         }
-        ++ic;
+        ++ic[0];
+        if (both) ++ic[1];
       }
     }
   } else {
 // ------------------------------ softmax + epilogue: thread = (query row of tile X, 64-key half) ------------------------------
-    const int k16 = warp - 3;
+    const int k16 = warp - 2;
     const int x = k16 >> 3;
     const int half = (k16 >> 2) & 1;
     const int quarter = warp & 3;
@@ -293,8 +323,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
           mk[t][k] = __ballot_sync(0xffffffffu, ok);
         }
       float m = -INFINITY, l = 0.f;   // l: partial row sum over this thread's columns
+#ifdef SIMVGB_FWD_TRACE
+      const bool tr = p.ts != nullptr && blockIdx.x == 0 && it == 0 && lane == 0 && quarter == 0 && half == 0;
+      const int tb = x * 256;
+#endif
       for (int j = 0; j < nk; ++j) {
+        FWD_TS(tr, tb + j * 8 + 0);
         mbar_wait(&s_full[x], sc & 1);
+        FWD_TS(tr, tb + j * 8 + 1);
         tc_fence_after();
         uint32_t s0[32], s1[32];
         tmem_ld32(tmS, s0);
@@ -303,6 +339,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[x]);   // scores are in registers: the MMA warp may overwrite S_X
+        FWD_TS(tr, tb + j * 8 + 2);
         if (j >= g.nfull) {
           const int t = j - g.nfull;
           const uint32_t ba = mk[t][0], bb = mk[t][1];
@@ -324,6 +361,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
         pair_sync(bar_id);
         mx3 = fmaxf(mx2, xm[(half ^ 1) * 128 + r]);
         ++sc;
+        FWD_TS(tr, tb + j * 8 + 3);
         const float mx = mx3 * kLog2e;
         const bool need = mx > m + 8.0f;       // lazy rescale threshold (log2 units); true on the first tile
         const float m_use = need ? mx : m;
@@ -332,7 +370,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
         uint32_t pk[16];
         // the first 32 exponentials need neither the P buffer nor O: they run while P_X(j-1) V_(j-1) is still on the tensor pipe
         float sum = exp_chunk<(SIMVGB_FWD_POLY > 0)>(s0, pk, neg_m);
+        if (SIMVGB_FWD_STAGGER && x == 0 && j == 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(mid);
+        }
+        FWD_TS(tr, tb + j * 8 + 4);
         mbar_wait(&pv_done[x], (pc & 1) ^ 1);  // P_X buffer free, O_X complete up to tile j-1
+        FWD_TS(tr, tb + j * 8 + 5);
         tc_fence_after();
         if (j > 0 && __any_sync(0xffffffffu, need)) {
 #pragma unroll 1
@@ -355,6 +399,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[x]);
         ++pc;
+        FWD_TS(tr, tb + j * 8 + 6);
       }
       // ------------------------------ epilogue ------------------------------
       float* xs = xrow + (sc & 1) * 256;      // the buffer tile nk would use: free (tile nk-2's readers passed tile nk-1's barrier)
@@ -437,6 +482,11 @@ extern "C" int simvgb_attn_fwd(const simvgb_attn_args* a, void* stream) {
   p.npairs = p.g.ntiles / 2;
   p.n_full_items = a->B * a->H * p.npairs;
   p.n_items = p.n_full_items + ((p.g.ntiles & 1) ? a->B * a->H : 0);
+#ifdef SIMVGB_FWD_TRACE
+  p.ts = g_fwd_trace;
+#else
+  p.ts = nullptr;
+#endif
   CUtensorMap full, tail, text;
   if (make_attn_maps(&full, &tail, &text, p.g, a->qkv_v, a->qkv_t, 3 * D)) return -1;
   if (ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_kernel), kFwdSmem)) return -2;
@@ -451,3 +501,7 @@ extern "C" int simvgb_attn_lse_stride(int Lv, int Lt) {
   simvgb::AttnGeom g = simvgb::make_attn_geom(1, 1, Lv, Lt, 64);
   return g.ntiles * simvgb::kTile;
 }
+
+#ifdef SIMVGB_FWD_TRACE
+extern "C" void simvgb_debug_attn_fwd_trace(long long* buf) { simvgb::g_fwd_trace = buf; }
+#endif

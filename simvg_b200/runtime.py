@@ -25,8 +25,9 @@ class GraphedTrainStep:
     (xyxy pixels) — host (ideally pinned) or device tensors.  The first call runs `warmup` forward+backward passes WITHOUT
     an optimiser step (allocator / workspace / NCCL warm-up: parameters, Adam moments and the step count are untouched, so
     the training trajectory equals the eager loop's) and captures; later calls with the same shapes and image sizes replay.
-    A new batch shape re-captures (again without touching the optimiser state).  Returned tensors are the graph's static
-    outputs (overwritten by the next call)."""
+    A new batch shape / image dtype captures another graph (again without touching the optimiser state); graphs are kept per
+    shape and share one memory pool, so alternating between shapes does not re-capture.  Returned tensors are the graph's
+    static outputs (overwritten by the next call with the same shape)."""
 
     def __init__(self, model, optimizer, ddp=None, warmup=1):
         self.model, self.opt, self.warmup = model, optimizer, max(1, int(warmup))
@@ -39,6 +40,9 @@ class GraphedTrainStep:
         self.static = None
         self.out = None
         self.launches_per_step = 0
+        self._cache = {}         # key -> (graph, graph_opt, static, out, launches, text-gradient mailbox)
+        self._pool = None
+        self._mail = None        # (ids, rows) tensors this graph's backward writes for the sparse text-embedding exchange
 
     def _fwd_bwd(self, d, metas):
         self.opt.zero_grad()
@@ -71,16 +75,22 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         # a process group's watchdog thread may touch CUDA while we capture: police this thread's calls only
         mode = "thread_local" if self.ddp is not None else "global"
-        with torch.cuda.graph(self.graph, stream=side, capture_error_mode=mode):   # same stream as the warm-up: autograd's AccumulateGrad nodes stay on it
+        kw = {} if self._pool is None else {"pool": self._pool}
+        with torch.cuda.graph(self.graph, stream=side, capture_error_mode=mode, **kw):   # same stream as the warm-up: autograd's AccumulateGrad nodes stay on it
             losses, preds = self._fwd_bwd(self.static, metas)
             if self.ddp is None:
                 self.opt.step()
+        if self._pool is None:
+            self._pool = self.graph.pool()
+        self.graph_opt = None
         if self.ddp is not None:
             self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt, stream=side, capture_error_mode=mode, pool=self.graph.pool()):
+            with torch.cuda.graph(self.graph_opt, stream=side, capture_error_mode=mode, pool=self._pool):
                 self.opt.step()
         self.launches_per_step = K.launch_count()
         self.out = (losses, preds)
+        st = getattr(getattr(self.model, "vis_enc", None), "sparse_text_grad", None)
+        self._mail = None if st is None else (st.get("ids"), st.get("rows"))
 
     def _upload(self, img, ids, mask, gt):
         self.static["img"].copy_(img, non_blocking=True)
@@ -92,10 +102,19 @@ class GraphedTrainStep:
         if not self.model.training:
             raise RuntimeError("GraphedTrainStep captures a training step: call model.train() first")
         key = (tuple(img.shape), img.dtype, tuple(ref_expr_inds.shape), tuple(tuple(m["img_shape"][:2]) for m in img_metas))
-        if self.graph is None or key != self.key:
+        if key != self.key:
+            if self.key is not None:
+                self._cache[self.key] = (self.graph, self.graph_opt, self.static, self.out, self.launches_per_step, self._mail)
             self.key = key
-            self._capture(img, ref_expr_inds, img_metas, text_attention_mask, gt_boxes)
-            # the capture pass itself does not execute: fall through and replay once for this batch
+            if key in self._cache:
+                self.graph, self.graph_opt, self.static, self.out, self.launches_per_step, self._mail = self._cache[key]
+                st = getattr(getattr(self.model, "vis_enc", None), "sparse_text_grad", None)
+                if st is not None and self._mail is not None:
+                    st["ids"], st["rows"] = self._mail      # the exchange reads the buffers THIS graph's backward fills
+                self._upload(img, ref_expr_inds, text_attention_mask, gt_boxes)
+            else:
+                self._capture(img, ref_expr_inds, img_metas, text_attention_mask, gt_boxes)
+                # the capture pass itself does not execute: fall through and replay once for this batch
         else:
             self._upload(img, ref_expr_inds, text_attention_mask, gt_boxes)
         self.opt.advance()
