@@ -97,9 +97,12 @@ typedef struct simvgb_attn_args {
   float* dq_acc_v;        /* fp32 workspace [B*Lv, H*64] (zeroed by the call) */
   float* dq_acc_t;        /* fp32 workspace [B*Lt, H*64] */
   float q_scale;          /* head_dim^-0.5, applied to dq on the way out */
+  int32_t delta_ready;    /* bwd: delta was already produced (simvgb_ln_bwd mode 1 with .delta set; non-token slots zero) */
 } simvgb_attn_args;
 
 int simvgb_attn_lse_stride(int Lv, int Lt);
+/* Position of text token 0 on the virtual sequence axis the lse / delta rows are indexed by (vision token i sits at i). */
+int simvgb_attn_text_offset(int Lv, int Lt);
 int simvgb_attn_fwd(const simvgb_attn_args* args, void* stream);
 int simvgb_attn_bwd(const simvgb_attn_args* args, void* stream);
 
@@ -138,6 +141,10 @@ typedef struct simvgb_ln_bwd_args {
   float* dbias_prev;      /* optional [C] accumulated (+=) */
   void* dx;               /* modes 1, 2: bf16 [rows, C] */
   const void* u;          /* mode 2: bf16 pre-activation */
+  /* mode 1, optional (NULL = off): the attention backward's delta = rowsum(O o dO) per head, written in simvgb_attn_bwd's
+   * workspace layout delta[(b * H + h) * delta_stride + delta_vbase + l] for row b * delta_L + l (x = O, dx = dO). */
+  float* delta;
+  int32_t delta_L, delta_H, delta_stride, delta_vbase;
 } simvgb_ln_bwd_args;
 int simvgb_ln_bwd(const simvgb_ln_bwd_args* args, void* stream);
 

@@ -151,6 +151,46 @@ def golden_head(nq, blw, name):
     torch.save(fx, os.path.join(OUT, name + ".pt"))
 
 
+def golden_interpolate():
+    """Reference BEIT3.load_model_and_may_interpolate (beit3.py:92-174): a 2x2-patch / P=32 checkpoint loaded into an 8x8-patch /
+    P=16 model -> bicubic position-embedding and patch-projection interpolation, run by the reference's own method."""
+    import importlib
+    import tempfile
+    b3 = importlib.import_module("simvg.models.vis_encs.beit.beit3")
+    torch.manual_seed(0)
+    ref = b3.BEIT3(img_size=128, patch_size=16, vit_type="base", drop_path_rate=0.0, vocab_size=64010, freeze_layer=-1,
+                   vision_embed_proj_interpolate=True, pretrain=None)
+    g = torch.Generator().manual_seed(13)
+    ck = {"beit3.encoder.embed_positions.A.weight": torch.randn(2 * 2 + 3, 768, generator=g),
+          "beit3.vision_embed.proj.weight": torch.randn(768, 3, 32, 32, generator=g) * 0.02,
+          "beit3.vision_embed.proj.bias": torch.randn(768, generator=g) * 0.02}
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "ck.pth")
+        torch.save({"model": {k: v.clone() for k, v in ck.items()}}, path)
+        ref.load_model_and_may_interpolate(path)
+    sd = ref.state_dict()
+    pe, pw = sd["beit3.encoder.embed_positions.A.weight"], sd["beit3.vision_embed.proj.weight"]
+    assert pe.shape == (8 * 8 + 3, 768) and pw.shape == (768, 3, 16, 16)
+    torch.save({"seed": 13, "pos_slice": pe[:, ::32].clone(), "pos_norm": float(pe.double().norm()),
+                "proj_slice": pw[::16, :, ::2, ::2].clone(), "proj_norm": float(pw.double().norm()),
+                "bias_norm": float(sd["beit3.vision_embed.proj.bias"].double().norm())}, os.path.join(OUT, "interpolate.pt"))
+    print("interpolate: pos", tuple(pe.shape), "proj", tuple(pw.shape))
+
+
+def golden_state_dict_keys():
+    """The reference model's full {state-dict key: shape} map (ViT-B/16 640 config and ViT-L/16), from the reference's own
+    build_model: the drop-in boundary requires set-equality (checkpoints are exchanged by key)."""
+    _, _, _, build_model = load_reference()
+    out = {}
+    for vit in ("base", "large"):
+        torch.manual_seed(0)
+        m = build_model(copy.deepcopy(model_cfg(vit, 640, 16, num_decoder_layers=3)))
+        out[vit] = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        del m
+    torch.save(out, os.path.join(OUT, "state_dict_keys.pt"))
+    print("state-dict keys:", {k: len(v) for k, v in out.items()})
+
+
 def golden_known_answers():
     """Quirk known-answer vectors computed by the reference's own heads/utils.py."""
     import importlib
@@ -173,4 +213,6 @@ if __name__ == "__main__":
     golden_head(10, {"decoder": 1.0, "balanced_distill": {"token": 1.0, "distill": 0.4}}, "head_nq10_dwbd")
     golden_head(1, {"decoder": 1.0}, "head_nq1_decoder_only")
     golden_cfg1()
+    golden_interpolate()
+    golden_state_dict_keys()
     print("golden fixtures written to", OUT)

@@ -585,9 +585,9 @@ extern "C" int simvgb_attn_bwd(const simvgb_attn_args* a, void* stream) {
     }
   }
 
-  // positions of the virtual axis that belong to neither token range are never written by the delta kernel: keep them 0
-  SIMVGB_CUDA(cudaMemsetAsync(a->delta, 0, sizeof(float) * (size_t)a->B * a->H * lse_stride, s));
-  {
+  if (!a->delta_ready) {
+    // positions of the virtual axis that belong to neither token range are never written by the delta kernel: keep them 0
+    SIMVGB_CUDA(cudaMemsetAsync(a->delta, 0, sizeof(float) * (size_t)a->B * a->H * lse_stride, s));
     const long long n = (long long)a->B * a->Lv * a->H;
     attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const bf16*>(a->out_v),
                                                                    reinterpret_cast<const bf16*>(a->dout_v), a->delta,

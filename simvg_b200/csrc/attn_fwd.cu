@@ -502,6 +502,8 @@ extern "C" int simvgb_attn_lse_stride(int Lv, int Lt) {
   return g.ntiles * simvgb::kTile;
 }
 
+extern "C" int simvgb_attn_text_offset(int Lv, int Lt) { return simvgb::make_attn_geom(1, 1, Lv, Lt, 64).T0; }
+
 #ifdef SIMVGB_FWD_TRACE
 extern "C" void simvgb_debug_attn_fwd_trace(long long* buf) { simvgb::g_fwd_trace = buf; }
 #endif

@@ -218,6 +218,10 @@ struct LnBwdParams {
   const bf16* u;         // mode 2
   long long R;
   int C, W, rpb, mode;
+  // mode 1 only (optional): delta[(b * H + h) * stride + vbase + l] = sum over head h's 64 columns of x * bf16(dx) for row b*L + l
+  // — the attention backward's rowsum(O o dO), produced here where O and dO are already in registers
+  float* delta;
+  int delta_L, delta_H, delta_stride, delta_vbase;
 };
 
 // Raw (still packed) operands of one row chunk: loaded one row ahead so the global-load latency of row i+1 overlaps the
@@ -387,6 +391,13 @@ __global__ void __launch_bounds__(128) ln_bwd_warp_kernel(const LnBwdParams p) {
     }
     const float mu = __ldg(p.mean + row), rs = __ldg(p.rstd + row);
     float s1 = 0.f, s2 = 0.f;
+    float xraw[MODE == 1 ? NCH : 1][8];
+    if (MODE == 1) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xraw[MODE == 1 ? c : 0][i] = xh[c][i];
+    }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
 #pragma unroll
@@ -418,6 +429,21 @@ __global__ void __launch_bounds__(128) ln_bwd_warp_kernel(const LnBwdParams p) {
         }
       } else {
         store8(p.dx + off, dx);
+        if (MODE == 1 && p.delta != nullptr) {
+          // lanes 8k .. 8k+7 hold the 64 columns of head 4c + k: three shuffles give the head's rowsum(O o dO), with dO rounded
+          // to bf16 exactly as it was just stored (the attention kernels read that rounded value)
+          float d = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d += xraw[MODE == 1 ? c : 0][i] * __bfloat162float(__float2bfloat16_rn(dx[i]));
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          if ((lane & 7) == 0) {
+            const long long bb = row / p.delta_L;
+            const int l = (int)(row - bb * p.delta_L);
+            p.delta[(bb * p.delta_H + (c * 4 + (lane >> 3))) * p.delta_stride + p.delta_vbase + l] = d;
+          }
+        }
       }
     }
   }
@@ -802,6 +828,12 @@ extern "C" int simvgb_ln_bwd(const simvgb_ln_bwd_args* a, void* stream) {
   p.rows_per_scale = a->rows_per_scale > 0 ? a->rows_per_scale : 1;
   p.dbias_prev = a->dbias_prev; p.dx = reinterpret_cast<bf16*>(a->dx); p.u = reinterpret_cast<const bf16*>(a->u);
   p.R = a->rows; p.C = a->C; p.W = W; p.rpb = rpb; p.mode = a->mode;
+  p.delta = a->delta; p.delta_L = a->delta_L; p.delta_H = a->delta_H; p.delta_stride = a->delta_stride; p.delta_vbase = a->delta_vbase;
+  if (p.delta != nullptr) {
+    SIMVGB_CHECK(a->mode == 1 && (a->C == 256 || a->C == 768 || a->C == 1024) && a->delta_H * 64 == a->C && a->delta_L > 0 &&
+                     a->rows % a->delta_L == 0,
+                 "simvgb_ln_bwd: delta needs mode 1, C = 64 * H in {256, 768, 1024} and rows = B * L");
+  }
   const int threads = 32 * W * rpb;
   const int grid = ln_grid(a->rows, rpb);
   const size_t sm = sizeof(float) * rpb * W * kLnMaxRB * 2;

@@ -68,7 +68,7 @@ class AttnArgs(ctypes.Structure):
         ("qkv_v", L.c_vp), ("qkv_t", L.c_vp), ("text_pad", L.c_vp),
         ("out_v", L.c_vp), ("out_t", L.c_vp), ("lse", L.c_vp),
         ("dout_v", L.c_vp), ("dout_t", L.c_vp), ("dqkv_v", L.c_vp), ("dqkv_t", L.c_vp),
-        ("delta", L.c_vp), ("dq_acc_v", L.c_vp), ("dq_acc_t", L.c_vp), ("q_scale", L.c_f32),
+        ("delta", L.c_vp), ("dq_acc_v", L.c_vp), ("dq_acc_t", L.c_vp), ("q_scale", L.c_f32), ("delta_ready", L.c_int),
     ]
 
 
@@ -81,6 +81,7 @@ class LnBwdArgs(ctypes.Structure):
         ("dres_in", L.c_vp), ("dres_out", L.c_vp), ("dyb", L.c_vp),
         ("row_scale", L.c_vp), ("rows_per_scale", L.c_int),
         ("dbias_prev", L.c_vp), ("dx", L.c_vp), ("u", L.c_vp),
+        ("delta", L.c_vp), ("delta_L", L.c_int), ("delta_H", L.c_int), ("delta_stride", L.c_int), ("delta_vbase", L.c_int),
     ]
 
 
@@ -92,6 +93,7 @@ def _lib_setup():
     lib = L.lib()
     if not getattr(lib, "_simvgb_typed", False):
         lib.simvgb_attn_lse_stride.restype = L.c_int
+        lib.simvgb_attn_text_offset.restype = L.c_int
         lib.simvgb_ln_fwd.argtypes = [L.c_vp, L.c_int, L.c_vp, L.c_int, L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_i64, L.c_int,
                                       L.c_f32, L.c_int, L.c_vp]
         lib.simvgb_colsum.argtypes = [L.c_vp, L.c_int, L.c_vp, L.c_vp, L.c_vp, L.c_int, L.c_i64, L.c_int, L.c_i64, L.c_vp]
@@ -246,7 +248,29 @@ def attn_fwd(qkv_v, qkv_t, pad, B, H, Lv, Lt):
     return out_v, out_t, lse
 
 
-def attn_bwd(qkv_v, qkv_t, pad, out_v, out_t, lse, dout_v, dout_t, B, H, Lv, Lt, ws=None):
+def attn_workspace(ws, B, H, Lv, Lt, dev):
+    """Backward workspaces (delta, fp32 dQ accumulators), cached per geometry in the dict `ws`.  delta is allocated ZEROED: its
+    non-token slots of the virtual sequence axis must read 0 and are never written."""
+    key = (B, H, Lv, Lt)
+    if ws.get("key") != key:
+        D = H * 64
+        ws["key"] = key
+        ws["delta"] = torch.zeros(B, H, attn_lse_stride(Lv, Lt), device=dev, dtype=f32)
+        ws["dq_v"] = torch.empty(B * Lv, D, device=dev, dtype=f32)
+        ws["dq_t"] = torch.empty(B * Lt, D, device=dev, dtype=f32)
+    return ws
+
+
+def attn_delta_spec(ws, B, H, Lv, Lt, which):
+    """`delta=` argument of ln_bwd(mode 1) for the vision (0) / text (1) rows: the inner-attention-LN backward then also emits
+    rowsum(O o dO) in the attention backward's layout, and attn_bwd(..., delta_ready=True) skips its own delta pass."""
+    stride = attn_lse_stride(Lv, Lt)
+    if which == 0:
+        return (ws["delta"], Lv, H, stride, 0)
+    return (ws["delta"], Lt, H, stride, _lib_setup().simvgb_attn_text_offset(Lv, Lt))
+
+
+def attn_bwd(qkv_v, qkv_t, pad, out_v, out_t, lse, dout_v, dout_t, B, H, Lv, Lt, ws=None, delta_ready=False):
     lib = _lib_setup()
     D = H * 64
     dev = qkv_v.device
@@ -254,19 +278,15 @@ def attn_bwd(qkv_v, qkv_t, pad, out_v, out_t, lse, dout_v, dout_t, B, H, Lv, Lt,
     dqkv_t = torch.empty(B * Lt, 3 * D, device=dev, dtype=bf16)
     if ws is None:
         ws = {}
-    key = (B, H, Lv, Lt)
-    if ws.get("key") != key:
-        ws["key"] = key
-        ws["delta"] = torch.empty(B, H, attn_lse_stride(Lv, Lt), device=dev, dtype=f32)
-        ws["dq_v"] = torch.empty(B * Lv, D, device=dev, dtype=f32)
-        ws["dq_t"] = torch.empty(B * Lt, D, device=dev, dtype=f32)
+    attn_workspace(ws, B, H, Lv, Lt, dev)
     a = _attn_args(B, H, Lv, Lt, qkv_v, qkv_t, pad, out_v, out_t, lse)
+    a.delta_ready = int(delta_ready)
     a.dout_v, a.dout_t = _p(dout_v), _p(dout_t)
     a.dqkv_v, a.dqkv_t = _p(dqkv_v), _p(dqkv_t)
     a.delta, a.dq_acc_v, a.dq_acc_t = _p(ws["delta"]), _p(ws["dq_v"]), _p(ws["dq_t"])
     with _timed("attn_bwd", 10.0 * B * H * (Lv + Lt) ** 2 * 64):
         L.check(lib.simvgb_attn_bwd(ctypes.byref(a), L.c_vp(_stream())), "attn_bwd")
-    _launches[0] += 5
+    _launches[0] += 3 if delta_ready else 5
     return dqkv_v, dqkv_t
 
 
@@ -285,7 +305,7 @@ def ln_fwd(x, gamma, beta, eps, out_dtype=bf16, gelu=False):
 
 
 def ln_bwd(mode, x, dy, gamma, mean, rstd, dgamma, dbeta, *, dres_in=None, dres_out=None, dyb=None, row_scale=None,
-           rows_per_scale=1, dbias_prev=None, dx=None, u=None):
+           rows_per_scale=1, dbias_prev=None, dx=None, u=None, delta=None):
     lib = _lib_setup()
     R, C = dy.shape
     a = LnBwdArgs()
@@ -296,6 +316,8 @@ def ln_bwd(mode, x, dy, gamma, mean, rstd, dgamma, dbeta, *, dres_in=None, dres_
     a.dres_in, a.dres_out, a.dyb = _p(dres_in), _p(dres_out), _p(dyb)
     a.row_scale, a.rows_per_scale = _p(row_scale), rows_per_scale
     a.dbias_prev, a.dx, a.u = _p(dbias_prev), _p(dx), _p(u)
+    if delta is not None:
+        a.delta, a.delta_L, a.delta_H, a.delta_stride, a.delta_vbase = delta[0].data_ptr(), delta[1], delta[2], delta[3], delta[4]
     L.check(lib.simvgb_ln_bwd(ctypes.byref(a), L.c_vp(_stream())), "ln_bwd")
     _launches[0] += 1
 

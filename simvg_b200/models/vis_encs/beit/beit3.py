@@ -431,12 +431,15 @@ def encoder_backward(mod, ctx, dxv, dxt):
         K.wgrad_pair(*[(dyb[g], svs[g]["a"], D, D, Rs[g], Gs[g].g["o_w"]) for g in range(2)])
         da = K.gemm_pair(*[(dyb[g], Gs[g].wb["o_w"], Rs[g], D, D, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
         dO = [torch.empty(Rs[g], D, device=dev, dtype=bf16) for g in range(2)]
+        ws = K.attn_workspace(mod._attn_ws, B, H, Lv, Lt, dev)
         for g, G in enumerate(Gs):
-            K.ln_bwd(1, svs[g]["o"], da[g], G.w["in_w"], svs[g]["mi"], svs[g]["ri"], G.g["in_w"], G.g["in_b"], dx=dO[g])
+            # the inner-attention-LN backward also emits delta = rowsum(O o dO) per head for the attention backward
+            K.ln_bwd(1, svs[g]["o"], da[g], G.w["in_w"], svs[g]["mi"], svs[g]["ri"], G.g["in_w"], G.g["in_b"], dx=dO[g],
+                     delta=K.attn_delta_spec(ws, B, H, Lv, Lt, g))
         del da
         svv, svt = svs
         dqkv = K.attn_bwd(svv["qkv"], svt["qkv"], ctx["pad"], svv["o"], svt["o"], sl["lse"], dO[0], dO[1], B, H, Lv, Lt,
-                          ws=mod._attn_ws)
+                          ws=ws, delta_ready=True)
         for g, G in enumerate(Gs):
             K.colsum(dqkv[g], out=G.gbqkv)
         K.wgrad_pair(*[(dqkv[g], svs[g]["h"], 3 * D, D, Rs[g], Gs[g].gWqkv) for g in range(2)])

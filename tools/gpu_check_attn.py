@@ -17,7 +17,7 @@ class AttnArgs(ctypes.Structure):
         ("qkv_v", L.c_vp), ("qkv_t", L.c_vp), ("text_pad", L.c_vp),
         ("out_v", L.c_vp), ("out_t", L.c_vp), ("lse", L.c_vp),
         ("dout_v", L.c_vp), ("dout_t", L.c_vp), ("dqkv_v", L.c_vp), ("dqkv_t", L.c_vp),
-        ("delta", L.c_vp), ("dq_acc_v", L.c_vp), ("dq_acc_t", L.c_vp), ("q_scale", L.c_f32),
+        ("delta", L.c_vp), ("dq_acc_v", L.c_vp), ("dq_acc_t", L.c_vp), ("q_scale", L.c_f32), ("delta_ready", L.c_int),
     ]
 
 
