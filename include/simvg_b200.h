@@ -183,6 +183,13 @@ int simvgb_adam_amsgrad_dev(float* p, const float* g, float* m, float* v, float*
                             float beta1, float beta2, float eps, float weight_decay, const float* grad_sumsq,
                             float max_norm, float* ema, void* stream);
 
+/* Hungarian matching on the device (detrex HungarianMatcher + scipy.optimize.linear_sum_assignment; called from
+ * simvg/core/criterion/criterion.py:226-271).  cost: fp32 [B, nq, ttot], sample b's targets are columns
+ * offsets[b] .. offsets[b+1]-1 (int32 [B+1], device); every sample needs nq <= 32 and <= 32 targets.  out_q / out_t: int64
+ * [B, kmax], the min(nq, n_b) assignments of sample b in ascending query order, padded with -1. */
+int simvgb_hungarian(const float* cost, int B, int nq, int ttot, const int32_t* offsets, int64_t* out_q, int64_t* out_t,
+                     int kmax, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,7 +4,8 @@ HungarianMatcher).
 Same interface as the reference (`SetCriterion(num_classes, matcher, weight_dict, eos_coef, loss_class_type)(outputs,
 targets)` with per-sample target dicts), but the REC case SimVG trains on — one query, one ground-truth box per sample —
 is matched without leaving the device: the assignment is the identity, so the reference's 6 `C.cpu()` + scipy round
-trips per step disappear.  Any other case (nq > 1, gREC multi-target) takes the exact scipy path.
+trips per step disappear.  Any other case (nq > 1, gREC multi-target) is solved by a device Hungarian kernel
+(simvgb_hungarian, csrc/matcher.cu; scipy is the test oracle and the path for CPU tensors).
 """
 from typing import List
 
@@ -40,14 +41,19 @@ class HungarianMatcher(nn.Module):
         if nq == 1 and all(s == 1 for s in sizes):  # identity assignment, no host sync
             z = torch.zeros(1, dtype=torch.int64, device=logits.device)
             return [(z, z) for _ in range(B)]
-        from scipy.optimize import linear_sum_assignment
         prob = logits.flatten(0, 1).softmax(-1)
         out_bbox = boxes.flatten(0, 1)
         tgt_ids = torch.cat([t["labels"] for t in targets])
         tgt_bbox = torch.cat([t["boxes"] for t in targets])
         C = self.cost_bbox * torch.cdist(out_bbox, tgt_bbox, p=1) + self.cost_class * (-prob[:, tgt_ids]) + \
             self.cost_giou * (-generalized_box_iou(box_cxcywh_to_xyxy(out_bbox), box_cxcywh_to_xyxy(tgt_bbox)))
-        C = C.view(B, nq, -1).cpu()
+        C = C.view(B, nq, -1)
+        if C.is_cuda and nq <= 32 and max(sizes, default=0) <= 32:
+            # the assignment is solved on the device (one thread per sample, simvgb_hungarian): no C.cpu() round trip
+            from simvg_b200 import kernels as K
+            return K.hungarian(C, sizes)
+        from scipy.optimize import linear_sum_assignment     # CPU tensors (tests) / oversized problems: the reference's path
+        C = C.cpu()
         idx = [linear_sum_assignment(c[i]) for i, c in enumerate(C.split(sizes, -1))]
         dev = logits.device
         return [(torch.as_tensor(i, dtype=torch.int64, device=dev), torch.as_tensor(j, dtype=torch.int64, device=dev))
@@ -121,10 +127,22 @@ class SetCriterion(nn.Module):
         from simvg_b200.core.box_ops import aligned_iou_giou
         num_boxes = float(len(targets))
         if is_dist_avail_and_initialized() and get_world_size() > 1:
-            # criterion.py:247-250 (all_reduce, / world, clamp(min=1)) kept on the device: no .item() sync, capturable
-            nb = torch.full((1,), num_boxes, dtype=torch.float, device=outputs["pred_logits"].device)
-            torch.distributed.all_reduce(nb)
-            num_boxes = torch.clamp(nb / get_world_size(), min=1.0)[0]
+            # criterion.py:247-250 (all_reduce, / world, clamp(min=1)) kept on the device: no .item() sync.  The value only
+            # depends on the ranks' batch sizes, so while a CUDA graph is being captured (simvg_b200.runtime: the step graphs
+            # contain NO collective) the result of the last eager evaluation with this local batch size is reused — the
+            # runtime's warm-up pass has run exactly that evaluation.
+            dev = outputs["pred_logits"].device
+            key = (int(num_boxes), str(dev))
+            cache = self.__dict__.setdefault("_num_boxes_cache", {})
+            if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+                if key not in cache:
+                    raise RuntimeError("SetCriterion: capturing a step graph before any eager step ran with this batch size")
+                num_boxes = cache[key]
+            else:
+                nb = torch.full((1,), num_boxes, dtype=torch.float, device=dev)
+                torch.distributed.all_reduce(nb)
+                num_boxes = torch.clamp(nb / get_world_size(), min=1.0)[0]
+                cache[key] = num_boxes
         else:
             num_boxes = max(num_boxes, 1.0)
         # Main output and every auxiliary decoder layer in ONE batched expression ([Ld, B, ...]): with a 6-layer decoder the

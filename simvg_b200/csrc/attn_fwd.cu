@@ -34,6 +34,9 @@ namespace simvgb {
 #ifndef SIMVGB_FWD_KS
 #define SIMVGB_FWD_KS 3
 #endif
+#ifndef SIMVGB_FWD_EXP16
+#define SIMVGB_FWD_EXP16 0    // 1: exponentials as ex2.approx.f16x2 (experiment: ptxas splits it into two MUFU.EX2.F16, see exp_chunk16)
+#endif
 #ifndef SIMVGB_FWD_STAGGER
 #define SIMVGB_FWD_STAGGER 0   // 1: hold tile B's first S product back until tile A is half-way through key tile 0 (anti-phase)
 #endif
@@ -111,6 +114,29 @@ __device__ __forceinline__ float exp_chunk(const uint32_t (&s)[32], uint32_t (&p
     pk[i] = pack_bf16x2(e0, e1);   // TMEM column c of P holds keys 2c (low half), 2c+1 (high half)
   }
   return sum0 + sum1;
+}
+
+// The same with half-precision exponentials: MUFU evaluates ex2.approx.f16x2 at the instruction rate of the fp32 form, i.e. two
+// exponentials per operation, and MUFU (16 / clk / SM) is what the softmax phases saturate at head_dim 64 (measured: 8.2 clk
+// per MUFU instruction and SM sub-partition during the exp phases).  Accuracy: the argument x = s*log2e - m (<= 8 by the lazy
+// rescaling) is rounded to fp16 — |x| < 16 keeps 2^x within 0.27 %, comparable to the bf16 rounding P gets anyway (0.2 %), and
+// such x carry weights < 2^-8 of the row maximum; fp16 results keep denormals (no flush: 2^-24 absolute resolution against a
+// row maximum >= 2^-8... 2^8), row sums are accumulated in fp32 from the very values that are packed into P.
+__device__ __forceinline__ float exp_chunk16(const uint32_t (&s)[32], uint32_t (&pk)[16], float neg_m) {
+  float2 acc = make_float2(0.f, 0.f);
+  const float2 sc = make_float2(kLog2e, kLog2e), nm = make_float2(neg_m, neg_m);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 x = fma2(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc, nm);
+    uint32_t h2, e2;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(x.y), "f"(x.x));       // {hi, lo} = {x.y, x.x}
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(e2) : "r"(h2));
+    float lo, hi;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(e2));
+    acc = add2(acc, make_float2(lo, hi));
+    pk[i] = pack_bf16x2(lo, hi);   // TMEM column c of P holds keys 2c (low half), 2c+1 (high half)
+  }
+  return acc.x + acc.y;
 }
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
@@ -369,7 +395,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
         const float neg_m = -m_use;
         uint32_t pk[16];
         // the first 32 exponentials need neither the P buffer nor O: they run while P_X(j-1) V_(j-1) is still on the tensor pipe
+#if SIMVGB_FWD_EXP16
+        float sum = exp_chunk16(s0, pk, neg_m);
+#else
         float sum = exp_chunk<(SIMVGB_FWD_POLY > 0)>(s0, pk, neg_m);
+#endif
         if (SIMVGB_FWD_STAGGER && x == 0 && j == 0) {
           __syncwarp();
           if (lane == 0) mbar_arrive(mid);
@@ -390,7 +420,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_const
           }
         }
         tmem_st16(tmP, pk);
+#if SIMVGB_FWD_EXP16
+        sum += exp_chunk16(s1, pk, neg_m);
+#else
         sum += exp_chunk<(SIMVGB_FWD_POLY > 0)>(s1, pk, neg_m);
+#endif
         tmem_st16(tmP + 16, pk);
         tmem_wait_st();
         l = l * alpha + sum;

@@ -384,6 +384,29 @@ def embed_text(table, ids, pad, posB, B, Lt, D):
     return xt
 
 
+def hungarian(cost, sizes):
+    """Per-sample optimal assignment on the device.  cost: fp32 [B, nq, sum(sizes)] (detrex HungarianMatcher's batched cost
+    matrix), sizes: host list of target counts.  -> [(query_idx, target_idx)] int64 device tensors per sample (scipy's
+    linear_sum_assignment order), with NO device->host synchronisation: the result lengths min(nq, n_b) are host-known."""
+    L.require_device(cost)
+    lib = _lib_setup()
+    B, nq, ttot = cost.shape
+    if max(sizes, default=0) > 32 or nq > 32:
+        raise RuntimeError("simvgb_hungarian handles at most 32 queries / 32 targets per sample (got nq=%d, max targets %d)" % (nq, max(sizes)))
+    off = [0]
+    for n in sizes:
+        off.append(off[-1] + int(n))
+    offsets = torch.tensor(off, dtype=torch.int32).to(cost.device, non_blocking=True)
+    kmax = max(1, min(nq, max(sizes, default=1)))
+    out_q = torch.empty(B, kmax, dtype=torch.int64, device=cost.device)
+    out_t = torch.empty(B, kmax, dtype=torch.int64, device=cost.device)
+    c = cost.contiguous().float()
+    L.check(lib.simvgb_hungarian(L.c_vp(c.data_ptr()), B, nq, ttot, L.c_vp(offsets.data_ptr()), L.c_vp(out_q.data_ptr()),
+                                 L.c_vp(out_t.data_ptr()), kmax, L.c_vp(_stream())), "hungarian")
+    _launches[0] += 1
+    return [(out_q[b, :min(nq, int(n))], out_t[b, :min(nq, int(n))]) for b, n in enumerate(sizes)]
+
+
 def sumsq(g, out):
     lib = _lib_setup()
     L.check(lib.simvgb_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "sumsq")

@@ -104,6 +104,10 @@ class TextGuidedQuerySelectKDDETRHead(nn.Module):
             wd.update(aux)
         self._pos_cache = {}
         self._wvec_cache = {}
+        # Token-branch-only inference (the deployment mode SimVG's paper argues for: the lightweight MLP branch alone).  The
+        # reference keeps a hard-coded `only_token=False` at tgqs_kd_detr_head.py:422; here it is an attribute: when True,
+        # forward_test skips input_proj, the position encodings and the whole object-token decoder.
+        self.only_token = False
 
     # ------------------------------------------------------------------------------------------ targets
     @staticmethod
@@ -215,11 +219,13 @@ class TextGuidedQuerySelectKDDETRHead(nn.Module):
         """x_mm: [B, C, h, w] (any strides; a channels-last view avoids a copy).  tgqs_kd_detr_head.py:375-454."""
         B, C, h, w = x_mm.shape
         nq, E = self.num_queries, self.embed_dim
-        mem_in = x_mm.permute(0, 2, 3, 1).reshape(B * h * w, C)
-        memory = ops.linear(mem_in, self.input_proj.weight.view(E, C), self.input_proj.bias).view(B, h * w, E)
+        token_only = self.only_token and not self.training
+        if not token_only:
+            mem_in = x_mm.permute(0, 2, 3, 1).reshape(B * h * w, C)
+            memory = ops.linear(mem_in, self.input_proj.weight.view(E, C), self.input_proj.bias).view(B, h * w, E)
+            img_masks, pos_embed = self.x_mask_pos_enc(B, (h, w), img_metas, x_mm.device)
         text_feat = self.input_text_proj(text_feat)
         cls_feat = self.input_cls_proj(cls_feat).unsqueeze(1)
-        img_masks, pos_embed = self.x_mask_pos_enc(B, (h, w), img_metas, x_mm.device)
         cls_feat = cls_feat.repeat((1, nq, 1))
         if self.text_guided_query_generation:
             # `~text_mask` on the loader's int64 mask is a bitwise NOT -> integer row gather (rows -1 / -2), Appendix C.1
@@ -247,6 +253,11 @@ class TextGuidedQuerySelectKDDETRHead(nn.Module):
             cls_tok = self.class_embed_token(cls_feat)
             coord_tok = self.bbox_embed_token(cls_feat).sigmoid()
             token_branch_output = {"pred_logits": cls_tok[-1], "pred_boxes": coord_tok[-1]}
+        if token_only:   # the reference's `only_token` branch (tgqs_kd_detr_head.py:434-441)
+            return {"token_branch_output": token_branch_output, "decoder_branch_output": {"pred_logits": None, "pred_boxes": None},
+                    "outputs_class_decoder_branch": None, "outputs_coord_decoder_branch": None,
+                    "outputs_class_token_branch": cls_tok, "outputs_coord_token_branch": coord_tok,
+                    "token_features": cls_feat, "decoder_features": None}
         hidden_states = self.transformer(memory, img_masks, query_embed, pos_embed)
         cls_dec = self.class_embed_decoder(hidden_states)
         coord_dec = self.bbox_embed_decoder(hidden_states).sigmoid()

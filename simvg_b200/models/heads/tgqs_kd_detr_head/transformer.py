@@ -55,6 +55,16 @@ class _Attention(nn.Module):
         Wq, Wk, Wv = self.attn.in_proj_weight.view(3, E, E).unbind(0)
         bq, bk, bv = self.attn.in_proj_bias.view(3, E).unbind(0)
         B, nq, nk = q_in.shape[0], q_in.shape[1], k_in.shape[1]
+        if nk == 1 and key_padding_mask is None:
+            # One key (the REC decoder's self-attention: a single object query attends to itself): softmax over one score is
+            # exactly 1 whatever q and k are, so out = out_proj(dropout(1) * v_proj(value)) and the q / k projections get exactly
+            # zero gradient — as they do in the reference, which computes all of it (A.9).  Saves ~35 tiny launches per layer.
+            v = F.linear(value, Wv, bv).view(B, 1, H, dh)
+            if self.training and self.attn_drop > 0:
+                v = v * F.dropout(torch.ones(B, 1, H, 1, device=v.device, dtype=v.dtype), p=self.attn_drop)
+            o = v.expand(B, nq, H, dh).reshape(B, nq, E)
+            o = F.linear(o, self.attn.out_proj.weight, self.attn.out_proj.bias)
+            return identity + o
         q = F.linear(q_in, Wq, bq).view(B, nq, H, dh) * (dh ** -0.5)
         if nk >= _ABSORB_MIN_KEYS and nq * H <= 128:
             o = self._absorbed(q, k_in, value, Wk, bk, Wv, bv, key_padding_mask)

@@ -191,7 +191,7 @@ class BEIT3(nn.Module):
 
     def load_model_and_may_interpolate(self, ckpt_path, model_key="model|module", model_prefix=""):
         """Checkpoint load with bicubic pos-embed / patch-proj interpolation (beit3.py:92-174)."""
-        ckpt = torch.load(ckpt_path, map_location="cpu")
+        ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)   # BEiT-3 releases are plain pickled dicts
         sd = None
         for key in model_key.split("|"):
             if key in ckpt:

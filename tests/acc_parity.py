@@ -1,9 +1,13 @@
-"""Acc@0.5 parity on held-out synthetic boxes (north_star): train the CUDA product and the CPU oracle (the reference's
-arithmetic) from IDENTICAL weights on IDENTICAL batches, then evaluate both on the same held-out batches.
+"""Acc@0.5 parity on held-out synthetic boxes (north_star): train the CUDA product and the oracle (the reference's arithmetic,
+plain eager fp32 PyTorch) from IDENTICAL weights on IDENTICAL batches, then evaluate both on the same held-out batches.
 
 Task: the box is recoverable from the image — a bright rectangle on N(0, 0.3^2) noise at the ground-truth box; text tokens are
-random.  Stochastic layers are off (eval-mode forward with losses, as in smoke()) so the two runs are comparable step by step.
-Writes gpurun_out/acc_parity.json.   python tests/acc_parity.py [steps] [batch] [img_size]
+random.  Both arms run on the GPU box: the product through its sm_100a kernels, the oracle as fp32 eager ops on cuda:0 with TF32
+off (the same code the CPU tests pin against the reference's files; on the device only so that thousands of steps are
+affordable).  Stochastic layers are off so the two runs are comparable step by step.  The encoder is the first `layers`
+ViT-B/16 layers (the task needs no depth; the oracle's cost scales with it).
+    python tests/acc_parity.py [steps] [batch] [img_size] [layers]        -> gpurun_out/acc_parity.json
+tests/test_gpu_acc_parity.py asserts on the result (both arms >= 80 %, |dAcc| <= 2 points, final-loss gap <= 5 %).
 """
 import copy
 import json
@@ -14,13 +18,12 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import simvg_oracle as O  # noqa: E402  (checker: lives under tests/ because only tests may use the oracle)
-from simvg_b200.models import build_model  # noqa: E402
-from simvg_b200.optim import FusedAdamAMSGrad  # noqa: E402
 from tools.synth import make_batch, model_cfg  # noqa: E402
 
+LR, LR_ENC, CLIP = 5e-4, 2e-4, 1.0
 
-def task_batch(B, S, seed):
+
+def task_batch(B, S, seed, device="cpu"):
     b = make_batch(B, S, seed=seed)
     g = torch.Generator().manual_seed(seed + 77)
     img = 0.3 * torch.randn(B, 3, S, S, generator=g)
@@ -28,83 +31,113 @@ def task_batch(B, S, seed):
         x0, y0, x1, y1 = [int(round(float(v))) for v in box]
         img[i, :, y0:y1 + 1, x0:x1 + 1] += 2.0
     b["img"] = img
+    if device != "cpu":
+        for k in ("img", "ref_expr_inds", "text_attention_mask"):
+            b[k] = b[k].to(device)
+        b["gt_bbox"] = [t.to(device) for t in b["gt_bbox"]]
     return b
 
 
-def main():
-    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 120
-    B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-    S = int(sys.argv[3]) if len(sys.argv) > 3 else 64
-    P, n_eval = 16, 8
-    lr, lr_enc, clip = 5e-4, 5e-5, 0.15
-    torch.manual_seed(6666)
+def build_arm_model(S, P, layers, seed=6666):
+    """-> (cfg, product model on CPU with its encoder truncated to `layers`, fp32 state dict of the same weights)."""
+    from simvg_b200.models import build_model
+    torch.manual_seed(seed)
     cfg = model_cfg("base", S, P, num_decoder_layers=3, drop_path_rate=0.0)
     model = build_model(cfg)
+    enc = model.vis_enc
+    enc.beit3.encoder.layers = torch.nn.ModuleList(list(enc.beit3.encoder.layers)[:layers])
+    enc.beit3.encoder.num_layers = layers
+    enc.cfg["layers"] = layers
+    enc.drop_path_probs = enc.drop_path_probs[:layers]
     sd0 = {k: v.detach().clone().float() for k, v in model.state_dict().items()}
+    return cfg, model, sd0
 
+
+def accuracy_at_05(pred, gt_list):
+    """apis/test.py:70-79 (mmdet aligned bbox_overlaps, eps 1e-6) batched on whatever device the boxes live on."""
+    gt = torch.stack(gt_list).to(pred)
+    lt, rb = torch.max(gt[:, :2], pred[:, :2]), torch.min(gt[:, 2:], pred[:, 2:])
+    wh = (rb - lt).clamp(min=0)
+    inter = wh[:, 0] * wh[:, 1]
+    a1 = (gt[:, 2] - gt[:, 0]) * (gt[:, 3] - gt[:, 1])
+    a2 = (pred[:, 2] - pred[:, 0]) * (pred[:, 3] - pred[:, 1])
+    return ((inter / (a1 + a2 - inter).clamp(min=1e-6)) >= 0.5).float().mean() * 100.0
+
+
+def run(steps=1500, B=32, S=128, layers=2, P=16, n_eval=8, log_every=100, out_path="gpurun_out/acc_parity.json"):
+    from oracle import simvg_oracle as O   # checker: this file lives under tests/ because only tests may use the oracle
+    from simvg_b200.optim import FusedAdamAMSGrad
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = "cuda"
+    cfg, model, sd0 = build_arm_model(S, P, layers)
     # ---- CUDA product
     model = model.cuda().eval()
-    opt = FusedAdamAMSGrad(model, lr=lr, lr_vis_enc=lr_enc, betas=(0.9, 0.98), eps=1e-9, grad_norm_clip=clip)
-    # ---- CPU oracle (reference arithmetic) + torch Adam(amsgrad) with the reference's two LR groups and clip
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "empty_weight" not in k) for k, v in sd0.items()}
+    opt = FusedAdamAMSGrad(model, lr=LR, lr_vis_enc=LR_ENC, betas=(0.9, 0.98), eps=1e-9, grad_norm_clip=CLIP)
+    # ---- oracle arm: reference arithmetic + torch Adam(amsgrad) with the reference's lr groups and clip
+    sd = {k: v.clone().to(dev).requires_grad_(v.dtype.is_floating_point and "empty_weight" not in k) for k, v in sd0.items()}
     params = [v for v in sd.values() if v.requires_grad]
-    ref_opt = torch.optim.Adam([{"params": [v for k, v in sd.items() if v.requires_grad and "vis_enc" in k], "lr": lr_enc},
-                                {"params": [v for k, v in sd.items() if v.requires_grad and "vis_enc" not in k], "lr": lr}],
+    ref_opt = torch.optim.Adam([{"params": [v for k, v in sd.items() if v.requires_grad and "vis_enc" in k], "lr": LR_ENC},
+                                {"params": [v for k, v in sd.items() if v.requires_grad and "vis_enc" not in k], "lr": LR}],
                                betas=(0.9, 0.98), eps=1e-9, weight_decay=0, amsgrad=True)
     om = O.OracleModel(sd, "base", S, P, cfg["head"])
+    om.cfg["layers"] = layers
 
     curve = []
-    t_gpu = t_cpu = 0.0
+    t_gpu = t_ref = 0.0
     for it in range(steps):
-        b = task_batch(B, S, seed=1000 + it)
+        b = task_batch(B, S, seed=1000 + it, device=dev)
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         opt.zero_grad()
-        losses, _ = model(b["img"].cuda(), b["ref_expr_inds"].cuda(), b["img_metas"], return_loss=True,
-                          text_attention_mask=b["text_attention_mask"].cuda(), gt_bbox=[t.cuda() for t in b["gt_bbox"]])
+        losses, _ = model(b["img"], b["ref_expr_inds"], b["img_metas"], return_loss=True,
+                          text_attention_mask=b["text_attention_mask"], gt_bbox=b["gt_bbox"])
         losses["loss_total"].backward()
         opt.step()
-        lg = float(losses["loss_total"])
+        lg = float(losses["loss_total"].detach())
         t_gpu += time.perf_counter() - t0
         t0 = time.perf_counter()
         ol, _, _ = om.forward_train(b["img"], b["ref_expr_inds"], copy.deepcopy(b["img_metas"]), b["text_attention_mask"], b["gt_bbox"])
         ref_opt.zero_grad()
         ol["loss_total"].backward()
-        torch.nn.utils.clip_grad_norm_(params, clip)
+        torch.nn.utils.clip_grad_norm_(params, CLIP)
         ref_opt.step()
-        lc = float(ol["loss_total"])
-        t_cpu += time.perf_counter() - t0
+        lc = float(ol["loss_total"].detach())
+        t_ref += time.perf_counter() - t0
         curve.append((lg, lc))
-        if it % 10 == 0 or it == steps - 1:
-            print("step %3d  loss cuda %.4f  oracle %.4f  rel %.2e" % (it, lg, lc, abs(lg - lc) / max(abs(lc), 1e-9)), flush=True)
+        if it % log_every == 0 or it == steps - 1:
+            print("step %4d  loss product %.4f  oracle %.4f  rel %.2e" % (it, lg, lc, abs(lg - lc) / max(abs(lc), 1e-9)), flush=True)
 
     # ---- held-out evaluation (fixed seeds never seen in training)
-    res = {"cuda": {"dec": [], "tok": []}, "oracle": {"dec": [], "tok": []}}
+    res = {"product": {"dec": [], "tok": []}, "oracle": {"dec": [], "tok": []}}
     box_diff = 0.0
     for j in range(n_eval):
-        b = task_batch(B, S, seed=900000 + j)
+        b = task_batch(B, S, seed=900000 + j, device=dev)
         with torch.no_grad():
-            pg = model(b["img"].cuda(), b["ref_expr_inds"].cuda(), b["img_metas"], return_loss=False,
-                       text_attention_mask=b["text_attention_mask"].cuda())
+            pg = model(b["img"], b["ref_expr_inds"], b["img_metas"], return_loss=False, text_attention_mask=b["text_attention_mask"])
         pc, _ = om.forward_test(b["img"], b["ref_expr_inds"], copy.deepcopy(b["img_metas"]), b["text_attention_mask"])
         for name, k in (("dec", 0), ("tok", 1)):
-            res["cuda"][name].append(float(O.accuracy_at_05(pg[k]["pred_bboxes"].cpu(), b["gt_bbox"])))
-            res["oracle"][name].append(float(O.accuracy_at_05(pc[k]["pred_bboxes"], b["gt_bbox"])))
-        box_diff = max(box_diff, float((pg[0]["pred_bboxes"].cpu() - pc[0]["pred_bboxes"]).abs().max()) / S)
+            res["product"][name].append(float(accuracy_at_05(pg[k]["pred_bboxes"], b["gt_bbox"])))
+            res["oracle"][name].append(float(accuracy_at_05(pc[k]["pred_bboxes"], b["gt_bbox"])))
+        box_diff = max(box_diff, float((pg[0]["pred_bboxes"] - pc[0]["pred_bboxes"]).abs().max()) / S)
     mean = lambda v: sum(v) / len(v)  # noqa: E731
-    out = {"steps": steps, "batch": B, "img_size": S, "patch": P, "held_out_images": n_eval * B,
-           "acc05_decoder": {"cuda": mean(res["cuda"]["dec"]), "oracle": mean(res["oracle"]["dec"])},
-           "acc05_token": {"cuda": mean(res["cuda"]["tok"]), "oracle": mean(res["oracle"]["tok"])},
-           "final_loss": {"cuda": curve[-1][0], "oracle": curve[-1][1]},
-           "first_loss": {"cuda": curve[0][0], "oracle": curve[0][1]},
-           "max_rel_loss_gap": max(abs(a - c) / max(abs(c), 1e-9) for a, c in curve),
+    tail = curve[-50:]
+    out = {"steps": steps, "batch": B, "img_size": S, "patch": P, "encoder_layers": layers, "held_out_images": n_eval * B,
+           "lr": LR, "lr_vis_enc": LR_ENC, "grad_norm_clip": CLIP,
+           "acc05_decoder": {"product": mean(res["product"]["dec"]), "oracle": mean(res["oracle"]["dec"])},
+           "acc05_token": {"product": mean(res["product"]["tok"]), "oracle": mean(res["oracle"]["tok"])},
+           "final_loss_mean50": {"product": mean([a for a, _ in tail]), "oracle": mean([c for _, c in tail])},
+           "first_loss": {"product": curve[0][0], "oracle": curve[0][1]},
+           "first_step_rel_loss_gap": abs(curve[0][0] - curve[0][1]) / abs(curve[0][1]),
            "max_pred_box_gap_frac_of_image": box_diff,
-           "seconds": {"cuda_train": t_gpu, "oracle_train": t_cpu}, "host_threads": os.cpu_count()}
-    os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/acc_parity.json", "w") as f:
+           "seconds": {"product_train": t_gpu, "oracle_train": t_ref}, "oracle_device": "cuda:0 eager fp32 (TF32 off)"}
+    os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+    with open(out_path, "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":
-    main()
+    a = [int(x) for x in sys.argv[1:]]
+    run(*a[:4])

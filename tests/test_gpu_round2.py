@@ -143,7 +143,8 @@ def _ddp_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from datetime import timedelta
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank), timeout=timedelta(seconds=90))
     from simvg_b200.optim import FlatDDP, FusedAdamAMSGrad
     from simvg_b200.runtime import GraphedTrainStep
     from tools.synth import make_batch
@@ -219,3 +220,38 @@ def test_two_gpu_gradient_exchange_equivalence(lib, tmp_path):
         assert res["overlap_err"] < 1e-4, res
         assert res["ranks_identical"], res
         assert res["graphs"] and res["graph_vs_eager_rel"] < 2e-3, res
+
+
+def test_device_hungarian_matches_scipy(lib):
+    """simvgb_hungarian against scipy.optimize.linear_sum_assignment (the reference's solver) on random rectangular problems:
+    more queries than targets, fewer, equal, empty target sets — identical assignments, ascending query order."""
+    from scipy.optimize import linear_sum_assignment
+    from simvg_b200 import kernels as K
+    g = torch.Generator().manual_seed(8)
+    for nq in (1, 3, 10, 32):
+        sizes = [int(x) for x in torch.randint(0, 8, (9,), generator=g)] + [nq, min(32, nq + 5), 1]
+        C = torch.randn(len(sizes), nq, sum(sizes), generator=g)
+        got = K.hungarian(C.cuda(), sizes)
+        off = 0
+        for b, n in enumerate(sizes):
+            r, c = linear_sum_assignment(C[b, :, off:off + n].double().numpy())
+            off += n
+            assert got[b][0].cpu().tolist() == list(r) and got[b][1].cpu().tolist() == list(c), (nq, b, n)
+
+
+def test_nq10_matcher_on_device_equals_scipy_path(lib):
+    """HungarianMatcher(nq = 10) on CUDA tensors (device kernel) returns what the scipy path returns on the same CPU tensors."""
+    from simvg_b200.core.criterion.criterion import HungarianMatcher
+    g = torch.Generator().manual_seed(9)
+    B, nq = 6, 10
+    logits, boxes = torch.randn(B, nq, 2, generator=g), torch.rand(B, nq, 4, generator=g) * 0.4 + 0.3
+    targets = []
+    for b in range(B):
+        n = 1 + b % 3
+        targets.append({"labels": torch.zeros(n, dtype=torch.int64), "boxes": torch.rand(n, 4, generator=g) * 0.3 + 0.3})
+    m = HungarianMatcher(cost_class=1, cost_bbox=5.0, cost_giou=2.0, cost_class_type="ce_cost")
+    want = m({"pred_logits": logits, "pred_boxes": boxes}, targets)
+    got = m({"pred_logits": logits.cuda(), "pred_boxes": boxes.cuda()},
+            [{k: v.cuda() for k, v in t.items()} for t in targets])
+    for (wq, wt), (gq, gt) in zip(want, got):
+        assert gq.is_cuda and wq.tolist() == gq.cpu().tolist() and wt.tolist() == gt.cpu().tolist()

@@ -334,3 +334,77 @@ def test_head_absorbed_attention_and_batched_losses_match_oracle():
     assert out["outputs_coord_decoder_branch"].shape[0] == 6
     rel_g = ((g_ours - x2.grad).norm() / x2.grad.norm()).item()
     assert rel_g < 1e-4, rel_g
+
+
+def test_state_dict_keys_equal_the_reference_exactly(golden_dir):
+    """Set-equality (names AND shapes) with the reference's own build_model state dict, ViT-B and ViT-L: checkpoints are
+    exchanged by key, so one missing / extra / mis-shaped entry breaks the drop-in (fixture: oracle/make_golden.py)."""
+    from simvg_b200.models import build_model
+    from tools.synth import model_cfg
+    want = torch.load(os.path.join(golden_dir, "state_dict_keys.pt"), weights_only=False)
+    for vit in ("base", "large"):
+        m = build_model(model_cfg(vit, 640, 16, num_decoder_layers=3))
+        got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert set(got) == set(want[vit]), (sorted(set(got) ^ set(want[vit]))[:10])
+        assert got == want[vit], [k for k in got if got[k] != want[vit][k]][:10]
+        del m
+
+
+def test_checkpoint_interpolation_matches_the_reference(golden_dir, tmp_path):
+    """BEIT3.load_model_and_may_interpolate against the reference's own method (beit3.py:92-174): a 2x2-patch, P=32 checkpoint
+    loaded into an 8x8-patch, P=16 model (bicubic position-embedding + patch-projection interpolation)."""
+    from simvg_b200.models.vis_encs.beit.beit3 import BEIT3
+    fx = torch.load(os.path.join(golden_dir, "interpolate.pt"), weights_only=False)
+    g = torch.Generator().manual_seed(fx["seed"])
+    ck = {"beit3.encoder.embed_positions.A.weight": torch.randn(2 * 2 + 3, 768, generator=g),
+          "beit3.vision_embed.proj.weight": torch.randn(768, 3, 32, 32, generator=g) * 0.02,
+          "beit3.vision_embed.proj.bias": torch.randn(768, generator=g) * 0.02}
+    path = str(tmp_path / "ck.pth")
+    torch.save({"model": ck}, path)
+    enc = BEIT3(img_size=128, patch_size=16, vit_type="base", drop_path_rate=0.0, vision_embed_proj_interpolate=True, pretrain=None)
+    enc.load_model_and_may_interpolate(path)
+    sd = enc.state_dict()
+    pe, pw = sd["beit3.encoder.embed_positions.A.weight"], sd["beit3.vision_embed.proj.weight"]
+    assert pe.shape == (67, 768) and pw.shape == (768, 3, 16, 16)
+    assert torch.allclose(pe[:, ::32], fx["pos_slice"], atol=1e-6) and abs(float(pe.double().norm()) - fx["pos_norm"]) < 1e-4 * fx["pos_norm"]
+    assert torch.allclose(pw[::16, :, ::2, ::2], fx["proj_slice"], atol=1e-7)
+    assert abs(float(pw.double().norm()) - fx["proj_norm"]) < 1e-4 * fx["proj_norm"]
+    assert abs(float(sd["beit3.vision_embed.proj.bias"].double().norm()) - fx["bias_norm"]) < 1e-5
+    # the constructor path (pretrain=<file>) goes through the same loader
+    enc2 = BEIT3(img_size=128, patch_size=16, vit_type="base", vision_embed_proj_interpolate=True, pretrain=path)
+    assert torch.equal(enc2.state_dict()["beit3.encoder.embed_positions.A.weight"], pe)
+
+
+def test_token_branch_only_inference_skips_the_decoder():
+    """head.only_token = True (the variable the reference hard-codes to False, tgqs_kd_detr_head.py:422): the token branch's
+    prediction is unchanged, the decoder branch returns the reference's `None` outputs and neither input_proj nor the decoder
+    runs."""
+    from simvg_b200.models.heads.tgqs_kd_detr_head.tgqs_kd_detr_head import TextGuidedQuerySelectKDDETRHead
+    from tools.synth import make_batch, model_cfg
+    hc = dict(model_cfg("base", 64, 32)["head"])
+    hc.pop("type")
+    hc["in_channels"] = 64
+    torch.manual_seed(0)
+    head = TextGuidedQuerySelectKDDETRHead(**hc).eval()
+    B = 2
+    x_mm, text, cls = torch.randn(B, 64, 2, 2), torch.randn(B, 20, 64), torch.randn(B, 64)
+    b = make_batch(B, 64)
+    metas = b["img_metas"]
+    for m in metas:
+        m["batch_input_shape"] = (64, 64)
+    import simvg_b200.ops as ops
+    real = ops.linear
+    ops.linear = lambda x, W, bias=None: torch.nn.functional.linear(x, W, bias)     # CPU stand-in for the tcgen05 GEMM
+    try:
+        with torch.no_grad():
+            full = head.forward_test(x_mm, metas, text_feat=text, cls_feat=cls, text_mask=b["text_attention_mask"])
+            head.only_token = True
+            calls = []
+            ops.linear = lambda *a, **k: calls.append(1)
+            tok = head.forward_test(x_mm, metas, text_feat=text, cls_feat=cls, text_mask=b["text_attention_mask"])
+    finally:
+        ops.linear = real
+    assert not calls
+    assert tok["decoder_branch_output"] == {"pred_logits": None, "pred_boxes": None} and tok["decoder_features"] is None
+    assert torch.equal(tok["token_branch_output"]["pred_boxes"], full["token_branch_output"]["pred_boxes"])
+    assert torch.equal(tok["token_branch_output"]["pred_logits"], full["token_branch_output"]["pred_logits"])
