@@ -82,6 +82,11 @@ def run(steps=1500, B=32, S=128, layers=2, P=16, n_eval=8, log_every=100, out_pa
                                betas=(0.9, 0.98), eps=1e-9, weight_decay=0, amsgrad=True)
     om = O.OracleModel(sd, "base", S, P, cfg["head"])
     om.cfg["layers"] = layers
+    # the reference's step schedule (core/scheduler.py: LambdaLR-style decay built ON the optimiser) drives both arms: x0.1 for
+    # the last 30 % of the steps, so both end converged instead of wherever their (chaotically diverging) trajectories happen to be
+    milestones = [int(0.7 * steps)]
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=milestones, gamma=0.1)
+    ref_sched = torch.optim.lr_scheduler.MultiStepLR(ref_opt, milestones=milestones, gamma=0.1)
 
     curve = []
     t_gpu = t_ref = 0.0
@@ -94,6 +99,7 @@ def run(steps=1500, B=32, S=128, layers=2, P=16, n_eval=8, log_every=100, out_pa
                           text_attention_mask=b["text_attention_mask"], gt_bbox=b["gt_bbox"])
         losses["loss_total"].backward()
         opt.step()
+        sched.step()
         lg = float(losses["loss_total"].detach())
         t_gpu += time.perf_counter() - t0
         t0 = time.perf_counter()
@@ -102,6 +108,7 @@ def run(steps=1500, B=32, S=128, layers=2, P=16, n_eval=8, log_every=100, out_pa
         ol["loss_total"].backward()
         torch.nn.utils.clip_grad_norm_(params, CLIP)
         ref_opt.step()
+        ref_sched.step()
         lc = float(ol["loss_total"].detach())
         t_ref += time.perf_counter() - t0
         curve.append((lg, lc))
