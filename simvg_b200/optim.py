@@ -122,6 +122,9 @@ class FusedAdamAMSGrad(torch.optim.Optimizer):
     # (beta^t is a running product updated by a tiny in-graph op), so replays need no per-step host->device traffic and the
     # host may run any number of steps ahead of the device.
     def enable_graph_mode(self):
+        """Idempotent: captured graphs bake the ADDRESSES of these scalars in, so they are created once and never replaced."""
+        if self.graph_mode and self._hyper is not None:
+            return
         dev = self.segments[0].fb.data.device
         n = len(self.segments)
         self._hyper = torch.zeros(n, 4, device=dev, dtype=torch.float32)
@@ -344,8 +347,9 @@ class FlatDDP:
         dist.all_gather_into_tensor(all_rows, rows.contiguous(), group=self.pg)
         fb = self._enc_seg.fb
         table = fb.grad_of(fb.names.index("text_embed"))
-        table.index_add_(0, all_ids, all_rows, alpha=1.0 / self.world)
-        st["ids"] = st["rows"] = None
+        # index_put_(accumulate=True) sorts the indices: duplicates are summed in a fixed order, so every rank (all hold the
+        # same gathered arrays) ends with bit-identical table gradients — index_add_'s atomics would let the replicas drift
+        table.index_put_((all_ids,), all_rows * (1.0 / self.world), accumulate=True)
 
     # ---- hooks called by the encoder backward (simvg_b200/models/vis_encs/beit/beit3.py), overlap mode only
     def on_encoder_backward_start(self):
