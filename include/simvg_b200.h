@@ -183,6 +183,105 @@ int simvgb_adam_amsgrad_dev(float* p, const float* g, float* m, float* v, float*
                             float beta1, float beta2, float eps, float weight_decay, const float* grad_sumsq,
                             float max_norm, float* ema, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Object-token head (fp32): fused building blocks of the DETR decoder layers, text-guided query generation and the MLP / class /
+ * box heads.  Replace detrex BaseTransformerLayer / MultiheadAttention / FFN over nn.Linear / nn.LayerNorm /
+ * nn.MultiheadAttention and their autograd graph (simvg/models/heads/tgqs_kd_detr_head/transformer.py:93-186,
+ * tgqs_kd_detr_head.py:375-454).  All buffers fp32 row-major; `drop_u` (optional) holds uniform [0,1) samples,
+ * an element is kept (and scaled by 1/(1-p)) iff u >= drop_p.  Backward entry points ACCUMULATE (+=) into every gradient buffer.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct simvgb_head_lin_args {
+  /* forward: y[r,n] = dropout(relu?( sum_k (x[r,k] + (n < n_split ? x2[r,k] : 0)) W[n,k] + b[n] ))
+   * k_splits > 1: partial sums are atomically added into a ZEROED y (bias from split 0), no relu / dropout.
+   * backward: dx (+ dx2 for the columns < n_split) += dY_eff W,  dW += dY_eff^T x_in,  db += colsum(dY_eff); NULL = skip. */
+  const float* x;        /* [R, K] */
+  const float* x2;       /* [R, K] or NULL (position embedding added to the input of the first n_split outputs) */
+  const float* W;        /* [N, K] */
+  const float* b;        /* [N] or NULL */
+  const float* drop_u;   /* [R, N] or NULL */
+  float* y;              /* [R, N] (backward: the forward output, needed for the ReLU mask) */
+  const float* dy;       /* [R, N] backward */
+  float* dx;             /* [R, K] */
+  float* dx2;            /* [R, K] */
+  float* dW;             /* [N, K] */
+  float* db;             /* [N] */
+  int32_t R, N, K, n_split, relu, k_splits;
+  float drop_p;
+} simvgb_head_lin_args;
+int simvgb_head_lin_fwd(const simvgb_head_lin_args* args, void* stream);
+int simvgb_head_lin_bwd(const simvgb_head_lin_args* args, void* stream);
+
+typedef struct simvgb_head_ln_args {
+  /* forward: s = a + dropout(b);  y = LayerNorm(s) * gamma + beta  (mean / rstd written).   C <= 512, multiple of 32.
+   * backward: ds = LN'(dy);  da += ds;  db += ds * dropmask;  dgamma += sum dy * xhat;  dbeta += sum dy. */
+  const float* a;        /* [R, C] */
+  const float* b;        /* [R, C] or NULL */
+  const float* drop_u;   /* [R, C] or NULL (applies to b) */
+  const float* gamma;
+  const float* beta;
+  float* y;
+  float* mean;           /* [R] forward: out, backward: in */
+  float* rstd;
+  const float* dy;
+  float* da;
+  float* db;
+  float* dgamma;
+  float* dbeta;
+  int32_t R, C;
+  float drop_p, eps;
+} simvgb_head_ln_args;
+int simvgb_head_lnres(const simvgb_head_ln_args* args, int backward, void* stream);
+
+typedef struct simvgb_head_attn_args {
+  /* Attention against at most 32 keys per sample (decoder self-attention over the nq queries; cross-attention of the
+   * text-guided query generation over the text tokens): H heads of 32 channels, scores = scale * q.k, key padding mask,
+   * softmax, dropout on the probabilities, ctx = P V.  q / k / v / ctx may be column slices (row strides ldq / ldk / ldc). */
+  const float* q;        /* rows b * nq + i */
+  const float* k;        /* rows b * nk + j */
+  const float* v;
+  const unsigned char* kpm;   /* [B, nk], 1 = ignore, or NULL */
+  const float* drop_u;   /* [B, H, nq, nk] or NULL */
+  float* ctx;
+  float* P;              /* [B, H, nq, nk] softmax before dropout (forward: out, backward: in) */
+  const float* dctx;
+  float* dq;
+  float* dk;
+  float* dv;
+  int32_t B, nq, nk, H, ldq, ldk, ldc;
+  float scale, drop_p;
+} simvgb_head_attn_args;
+int simvgb_head_attn_small(const simvgb_head_attn_args* args, int backward, void* stream);
+
+typedef struct simvgb_head_xattn_args {
+  /* Cross-attention of nq queries against the N-token image memory with the key / value projections absorbed into the query /
+   * output side: s[h,n] = (Wk_h^T q_h) . kin[b,n] + q_h . bk_h;  ctx_h = Wv_h (sum_n pd[h,n] val[b,n]) + bv_h sum_n pd[h,n].
+   * E = 256, H = 8.  q is the projected, scaled query [B*nq, E]; kin = memory + positions, val = memory: [B, N, E]. */
+  const float* q;
+  const float* kin;
+  const float* val;
+  const float* Wk;       /* [E, E] rows = output channel (the k block of in_proj_weight) */
+  const float* bk;
+  const float* Wv;
+  const float* bv;
+  const unsigned char* kpm;   /* [B, N] or NULL */
+  const float* drop_u;   /* [B*nq, H, N] or NULL */
+  float* ctx;            /* [B*nq, E] */
+  float* P;              /* [B*nq, H, N] */
+  float* z;              /* [B*nq, H, E] */
+  float* psum;           /* [B*nq, H] */
+  const float* dctx;
+  float* dq;
+  float* dkin;
+  float* dval;
+  float* dWk;
+  float* dbk;
+  float* dWv;
+  float* dbv;
+  int32_t B, nq, N, E, H;
+  float drop_p;
+} simvgb_head_xattn_args;
+int simvgb_head_xattn(const simvgb_head_xattn_args* args, int backward, void* stream);
+
 /* Hungarian matching on the device (detrex HungarianMatcher + scipy.optimize.linear_sum_assignment; called from
  * simvg/core/criterion/criterion.py:226-271).  cost: fp32 [B, nq, ttot], sample b's targets are columns
  * offsets[b] .. offsets[b+1]-1 (int32 [B+1], device); every sample needs nq <= 32 and <= 32 targets.  out_q / out_t: int64

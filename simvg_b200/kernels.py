@@ -430,3 +430,161 @@ def adam_amsgrad_dev(p, g, m, v, vmax, hyper, beta1, beta2, eps, weight_decay, g
                                         hyper.data_ptr(), beta1, beta2, eps, weight_decay, _p(grad_sumsq), max_norm, _p(ema),
                                         _stream()), "adam_amsgrad_dev")
     _launches[0] += 1
+
+
+# ---------------------------------------------------------------------------------------------- object-token head (fp32)
+class HeadLinArgs(ctypes.Structure):
+    _fields_ = [("x", L.c_vp), ("x2", L.c_vp), ("W", L.c_vp), ("b", L.c_vp), ("drop_u", L.c_vp), ("y", L.c_vp), ("dy", L.c_vp),
+                ("dx", L.c_vp), ("dx2", L.c_vp), ("dW", L.c_vp), ("db", L.c_vp),
+                ("R", L.c_int), ("N", L.c_int), ("K", L.c_int), ("n_split", L.c_int), ("relu", L.c_int), ("k_splits", L.c_int),
+                ("drop_p", L.c_f32)]
+
+
+class HeadLnArgs(ctypes.Structure):
+    _fields_ = [("a", L.c_vp), ("b", L.c_vp), ("drop_u", L.c_vp), ("gamma", L.c_vp), ("beta", L.c_vp), ("y", L.c_vp),
+                ("mean", L.c_vp), ("rstd", L.c_vp), ("dy", L.c_vp), ("da", L.c_vp), ("db", L.c_vp), ("dgamma", L.c_vp),
+                ("dbeta", L.c_vp), ("R", L.c_int), ("C", L.c_int), ("drop_p", L.c_f32), ("eps", L.c_f32)]
+
+
+class HeadAttnArgs(ctypes.Structure):
+    _fields_ = [("q", L.c_vp), ("k", L.c_vp), ("v", L.c_vp), ("kpm", L.c_vp), ("drop_u", L.c_vp), ("ctx", L.c_vp), ("P", L.c_vp),
+                ("dctx", L.c_vp), ("dq", L.c_vp), ("dk", L.c_vp), ("dv", L.c_vp),
+                ("B", L.c_int), ("nq", L.c_int), ("nk", L.c_int), ("H", L.c_int), ("ldq", L.c_int), ("ldk", L.c_int), ("ldc", L.c_int),
+                ("scale", L.c_f32), ("drop_p", L.c_f32)]
+
+
+class HeadXAttnArgs(ctypes.Structure):
+    _fields_ = [("q", L.c_vp), ("kin", L.c_vp), ("val", L.c_vp), ("Wk", L.c_vp), ("bk", L.c_vp), ("Wv", L.c_vp), ("bv", L.c_vp),
+                ("kpm", L.c_vp), ("drop_u", L.c_vp), ("ctx", L.c_vp), ("P", L.c_vp), ("z", L.c_vp), ("psum", L.c_vp),
+                ("dctx", L.c_vp), ("dq", L.c_vp), ("dkin", L.c_vp), ("dval", L.c_vp), ("dWk", L.c_vp), ("dbk", L.c_vp),
+                ("dWv", L.c_vp), ("dbv", L.c_vp),
+                ("B", L.c_int), ("nq", L.c_int), ("N", L.c_int), ("E", L.c_int), ("H", L.c_int), ("drop_p", L.c_f32)]
+
+
+def _f32c(t):
+    """fp32, contiguous (the head kernels take plain row-major fp32 buffers)."""
+    if t is None:
+        return None
+    assert t.dtype == f32 and t.is_contiguous(), (t.dtype, t.shape, t.stride())
+    return t
+
+
+def head_lin_fwd(x, W, b=None, x2=None, n_split=0, relu=False, drop_u=None, drop_p=0.0, k_splits=1, out=None):
+    """y = dropout(relu?((x + x2 [first n_split outputs only]) W^T + b)); x [R, K], W [N, K] -> [R, N]."""
+    L.require_device(x)
+    lib = _lib_setup()
+    R, Kd = x.shape
+    N = W.shape[0]
+    if out is None:
+        out = (torch.zeros if k_splits > 1 else torch.empty)(R, N, device=x.device, dtype=f32)
+    a = HeadLinArgs()
+    a.x, a.x2, a.W, a.b, a.drop_u, a.y = _p(_f32c(x)), _p(_f32c(x2)), _p(_f32c(W)), _p(b), _p(drop_u), out.data_ptr()
+    a.R, a.N, a.K, a.n_split, a.relu, a.k_splits, a.drop_p = R, N, Kd, (N if x2 is not None and n_split <= 0 else n_split), int(relu), k_splits, drop_p
+    L.check(lib.simvgb_head_lin_fwd(ctypes.byref(a), L.c_vp(_stream())), "head_lin_fwd")
+    _launches[0] += 1
+    return out
+
+
+def head_lin_bwd(dy, x, W, *, y=None, x2=None, n_split=0, relu=False, drop_u=None, drop_p=0.0, dx=None, dx2=None, dW=None, db=None):
+    """Accumulates dx (+ dx2) += dY_eff W, dW += dY_eff^T (x [+ x2]), db += colsum(dY_eff)."""
+    lib = _lib_setup()
+    R, Kd = x.shape
+    N = W.shape[0]
+    a = HeadLinArgs()
+    a.x, a.x2, a.W, a.drop_u, a.y, a.dy = _p(_f32c(x)), _p(_f32c(x2)), _p(_f32c(W)), _p(drop_u), _p(y), _p(_f32c(dy))
+    a.dx, a.dx2, a.dW, a.db = _p(dx), _p(dx2), _p(dW), _p(db)
+    a.R, a.N, a.K, a.n_split, a.relu, a.k_splits, a.drop_p = R, N, Kd, (N if x2 is not None and n_split <= 0 else n_split), int(relu), 1, drop_p
+    L.check(lib.simvgb_head_lin_bwd(ctypes.byref(a), L.c_vp(_stream())), "head_lin_bwd")
+    _launches[0] += (1 if dW is not None else 0) + (0 if dx is None and dx2 is None else (2 if (x2 is not None and a.n_split < N) else 1))
+
+
+def head_lnres_fwd(a_in, b_in, gamma, beta, eps=1e-5, drop_u=None, drop_p=0.0):
+    """y = LN(a + dropout(b)) -> (y, mean, rstd)."""
+    L.require_device(a_in)
+    lib = _lib_setup()
+    R, C = a_in.shape
+    y = torch.empty_like(a_in)
+    mean = torch.empty(R, device=a_in.device, dtype=f32)
+    rstd = torch.empty(R, device=a_in.device, dtype=f32)
+    a = HeadLnArgs()
+    a.a, a.b, a.drop_u, a.gamma, a.beta, a.y, a.mean, a.rstd = _p(_f32c(a_in)), _p(_f32c(b_in)), _p(drop_u), _p(gamma), _p(beta), y.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    a.R, a.C, a.drop_p, a.eps = R, C, drop_p, eps
+    L.check(lib.simvgb_head_lnres(ctypes.byref(a), 0, L.c_vp(_stream())), "head_lnres_fwd")
+    _launches[0] += 1
+    return y, mean, rstd
+
+
+def head_lnres_bwd(dy, a_in, b_in, gamma, mean, rstd, dgamma, dbeta, da=None, db=None, drop_u=None, drop_p=0.0, eps=1e-5):
+    lib = _lib_setup()
+    R, C = a_in.shape
+    a = HeadLnArgs()
+    a.a, a.b, a.drop_u, a.gamma, a.mean, a.rstd, a.dy = _p(_f32c(a_in)), _p(_f32c(b_in)), _p(drop_u), _p(gamma), mean.data_ptr(), rstd.data_ptr(), _p(_f32c(dy))
+    a.da, a.db, a.dgamma, a.dbeta = _p(da), _p(db), dgamma.data_ptr(), dbeta.data_ptr()
+    a.R, a.C, a.drop_p, a.eps = R, C, drop_p, eps
+    L.check(lib.simvgb_head_lnres(ctypes.byref(a), 1, L.c_vp(_stream())), "head_lnres_bwd")
+    _launches[0] += 1
+
+
+def _attn_small_args(q, k, v, B, nq, nk, H, ldq, ldk, ldc, scale, kpm, drop_u, drop_p):
+    a = HeadAttnArgs()
+    a.q, a.k, a.v, a.kpm, a.drop_u = q.data_ptr(), k.data_ptr(), v.data_ptr(), _p(kpm), _p(drop_u)
+    a.B, a.nq, a.nk, a.H, a.ldq, a.ldk, a.ldc, a.scale, a.drop_p = B, nq, nk, H, ldq, ldk, ldc, scale, drop_p
+    return a
+
+
+def head_attn_small_fwd(q, k, v, B, nq, nk, H, scale, kpm=None, drop_u=None, drop_p=0.0):
+    """q [B*nq, *], k / v [B*nk, *] (2-D views with unit column stride; row strides may differ: packed projections) -> ctx [B*nq, H*32], P."""
+    L.require_device(q)
+    lib = _lib_setup()
+    ctx = torch.empty(B * nq, H * 32, device=q.device, dtype=f32)
+    P = torch.empty(B, H, nq, nk, device=q.device, dtype=f32)
+    assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1 and k.stride(0) == v.stride(0)
+    a = _attn_small_args(q, k, v, B, nq, nk, H, q.stride(0), k.stride(0), ctx.stride(0), scale, kpm, drop_u, drop_p)
+    a.ctx, a.P = ctx.data_ptr(), P.data_ptr()
+    L.check(lib.simvgb_head_attn_small(ctypes.byref(a), 0, L.c_vp(_stream())), "head_attn_small_fwd")
+    _launches[0] += 1
+    return ctx, P
+
+
+def head_attn_small_bwd(dctx, q, k, v, P, dq, dk, dv, B, nq, nk, H, scale, drop_u=None, drop_p=0.0):
+    """Accumulates into dq / dk / dv (views with the same strides as q / k / v)."""
+    lib = _lib_setup()
+    assert dq.stride(0) == q.stride(0) and dk.stride(0) == k.stride(0) and dv.stride(0) == k.stride(0) and dctx.is_contiguous()
+    a = _attn_small_args(q, k, v, B, nq, nk, H, q.stride(0), k.stride(0), dctx.stride(0), scale, None, drop_u, drop_p)
+    a.P, a.dctx, a.dq, a.dk, a.dv = P.data_ptr(), dctx.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    L.check(lib.simvgb_head_attn_small(ctypes.byref(a), 1, L.c_vp(_stream())), "head_attn_small_bwd")
+    _launches[0] += 1
+
+
+def _xattn_args(q, kin, val, Wk, bk, Wv, bv, B, nq, N, kpm, drop_u, drop_p):
+    a = HeadXAttnArgs()
+    a.q, a.kin, a.val = _p(_f32c(q)), _p(_f32c(kin)), _p(_f32c(val))
+    a.Wk, a.bk, a.Wv, a.bv = _p(_f32c(Wk)), _p(_f32c(bk)), _p(_f32c(Wv)), _p(_f32c(bv))
+    a.kpm, a.drop_u, a.B, a.nq, a.N, a.E, a.H, a.drop_p = _p(kpm), _p(drop_u), B, nq, N, 256, 8, drop_p
+    return a
+
+
+def head_xattn_fwd(q, kin, val, Wk, bk, Wv, bv, B, nq, N, kpm=None, drop_u=None, drop_p=0.0):
+    """Absorbed-projection cross-attention over the image memory -> (ctx [B*nq, 256], P [B*nq, 8, N], z [B*nq, 8, 256], psum [B*nq, 8])."""
+    L.require_device(q)
+    lib = _lib_setup()
+    R = B * nq
+    ctx = torch.empty(R, 256, device=q.device, dtype=f32)
+    P = torch.empty(R, 8, N, device=q.device, dtype=f32)
+    z = torch.empty(R, 8, 256, device=q.device, dtype=f32)
+    psum = torch.empty(R, 8, device=q.device, dtype=f32)
+    a = _xattn_args(q, kin, val, Wk, bk, Wv, bv, B, nq, N, kpm, drop_u, drop_p)
+    a.ctx, a.P, a.z, a.psum = ctx.data_ptr(), P.data_ptr(), z.data_ptr(), psum.data_ptr()
+    L.check(lib.simvgb_head_xattn(ctypes.byref(a), 0, L.c_vp(_stream())), "head_xattn_fwd")
+    _launches[0] += 1
+    return ctx, P, z, psum
+
+
+def head_xattn_bwd(dctx, q, kin, val, Wk, bk, Wv, bv, P, z, psum, B, nq, N, dq, dkin, dval, dWk, dbk, dWv, dbv, kpm=None, drop_u=None,
+                   drop_p=0.0):
+    lib = _lib_setup()
+    a = _xattn_args(q, kin, val, Wk, bk, Wv, bv, B, nq, N, kpm, drop_u, drop_p)
+    a.P, a.z, a.psum, a.dctx = P.data_ptr(), z.data_ptr(), psum.data_ptr(), _p(_f32c(dctx))
+    a.dq, a.dkin, a.dval, a.dWk, a.dbk, a.dWv, a.dbv = (t.data_ptr() for t in (dq, dkin, dval, dWk, dbk, dWv, dbv))
+    L.check(lib.simvgb_head_xattn(ctypes.byref(a), 1, L.c_vp(_stream())), "head_xattn_bwd")
+    _launches[0] += 1

@@ -75,12 +75,14 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         # a process group's watchdog thread may touch CUDA while we capture: police this thread's calls only
         mode = "thread_local" if self.ddp is not None else "global"
-        kw = {} if self._pool is None else {"pool": self._pool}
+        # graphs of different input shapes share one memory pool when they are the only thing running between replays; with a
+        # process group the eager exchange sits between the two graphs of a step, so every shape keeps its own pool there
+        kw = {} if (self._pool is None or self.ddp is not None) else {"pool": self._pool}
         with torch.cuda.graph(self.graph, stream=side, capture_error_mode=mode, **kw):   # same stream as the warm-up: autograd's AccumulateGrad nodes stay on it
             losses, preds = self._fwd_bwd(self.static, metas)
             if self.ddp is None:
                 self.opt.step()
-        if self._pool is None:
+        if self._pool is None or self.ddp is not None:
             self._pool = self.graph.pool()
         self.graph_opt = None
         if self.ddp is not None:
