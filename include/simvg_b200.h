@@ -255,7 +255,7 @@ int simvgb_head_attn_small(const simvgb_head_attn_args* args, int backward, void
 typedef struct simvgb_head_xattn_args {
   /* Cross-attention of nq queries against the N-token image memory with the key / value projections absorbed into the query /
    * output side: s[h,n] = (Wk_h^T q_h) . kin[b,n] + q_h . bk_h;  ctx_h = Wv_h (sum_n pd[h,n] val[b,n]) + bv_h sum_n pd[h,n].
-   * E = 256, H = 8.  q is the projected, scaled query [B*nq, E]; kin = memory + positions, val = memory: [B, N, E]. */
+   * E = 256, H = 8.  q is the projected (unscaled) query [B*nq, E]; kin = memory + positions, val = memory: [B, N, E]. */
   const float* q;
   const float* kin;
   const float* val;
@@ -279,6 +279,7 @@ typedef struct simvgb_head_xattn_args {
   float* dbv;
   int32_t B, nq, N, E, H;
   float drop_p;
+  float scale;           /* head_dim^-0.5, applied to q inside */
 } simvgb_head_xattn_args;
 int simvgb_head_xattn(const simvgb_head_xattn_args* args, int backward, void* stream);
 

@@ -142,11 +142,12 @@ class SetCriterion(nn.Module):
                 nb = torch.full((1,), num_boxes, dtype=torch.float, device=dev)
                 torch.distributed.all_reduce(nb)
                 nb = torch.clamp(nb / get_world_size(), min=1.0)
-                if key in cache:
-                    cache[key].copy_(nb[0])     # in place: a captured step graph may hold this tensor's address
-                else:
-                    cache[key] = nb[0].clone()
-                num_boxes = cache[key]
+                num_boxes = nb[0]               # this (eager) evaluation uses its own tensor: autograd saves it
+                with torch.no_grad():
+                    if key in cache:
+                        cache[key].copy_(nb[0])     # in place: a captured step graph may hold the cached tensor's address
+                    else:
+                        cache[key] = nb[0].clone()
         else:
             num_boxes = max(num_boxes, 1.0)
         # Main output and every auxiliary decoder layer in ONE batched expression ([Ld, B, ...]): with a 6-layer decoder the

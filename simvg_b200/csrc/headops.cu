@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(128) attn_small_bwd_kernel(const AttnSmall p) 
 // Few queries against the long image memory (N ~ 1600 keys, E = 256, H = 8 heads of 32): the key / value projections are absorbed
 // into the query / output side, so the projected keys and values are never formed (simvg_b200 transformer.py::_absorbed; same
 // arithmetic as nn.MultiheadAttention, reassociated):
-//     u[h]   = Wk_h^T q_h            c[h] = q_h . bk_h               (q already scaled)
+//     u[h]   = Wk_h^T q_h            c[h] = q_h . bk_h               (q = scale * the projected query)
 //     s[h,n] = u[h] . kin[b,n] + c[h]         p = softmax_n(s)  (key padding mask),  pd = dropout(p)
 //     z[h]   = sum_n pd[h,n] val[b,n]         ctx_h = Wv_h z[h] + bv_h sum_n pd[h,n]
 // One CTA (256 threads = 8 warps, warp w = head w) per (b, i): the memory rows of sample b are read once per pass for all heads.
@@ -359,7 +359,7 @@ struct XAttn {
   float *ctx, *P, *z, *psum;   // P [R, H, N] (pre-dropout), z [R, H, E], psum [R, H]
   float *dq, *dkin, *dval, *dWk, *dbk, *dWv, *dbv;
   int B, nq, N, E, H;
-  float drop_p;
+  float drop_p, scale;
 };
 
 __global__ void __launch_bounds__(256) xattn_fwd_kernel(const XAttn p) {
@@ -378,14 +378,14 @@ __global__ void __launch_bounds__(256) xattn_fwd_kernel(const XAttn p) {
     float acc = 0.f;
 #pragma unroll 8
     for (int d = 0; d < 32; ++d) acc = fmaf(q[h * 32 + d], p.Wk[(long long)(h * 32 + d) * E + e], acc);
-    u[idx] = acc;
+    u[idx] = acc * p.scale;
     zs[idx] = 0.f;
   }
   __syncthreads();
   const int h = warp;                  // H == 8 == warps
   float c = 0.f;
   for (int d = lane; d < 32; d += 32) c += q[h * 32 + d] * p.bk[h * 32 + d];
-  c = warp_sum(c);
+  c = warp_sum(c) * p.scale;
   // pass 1: scores -> P buffer (raw), running max
   float* Prow = p.P + ((long long)row * H + h) * N;
   float uh[8];
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XAttn p) {
       a = fmaf(q[h * 32 + d], p.Wk[(long long)(h * 32 + d) * E + e], a);
       g = fmaf(dctx[h * 32 + d], p.Wv[(long long)(h * 32 + d) * E + e], g);
     }
-    u[idx] = a;
+    u[idx] = a * p.scale;
     dz[idx] = g;
     du_s[idx] = 0.f;
   }
@@ -550,14 +550,14 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XAttn p) {
     const int o = threadIdx.x, hh = o / 32;
     const float* wr = p.Wk + (long long)o * E;
     float* dwr = p.dWk + (long long)o * E;
-    const float qo = q[o];
+    const float qo = q[o] * p.scale;
     float acc = 0.f;
     for (int e = 0; e < E; ++e) {
       const float g = du_s[hh * E + e];
       acc = fmaf(g, wr[e], acc);
       atomicAdd(dwr + e, qo * g);
     }
-    atomicAdd(p.dq + (long long)row * E + o, acc + sc[hh] * p.bk[o]);
+    atomicAdd(p.dq + (long long)row * E + o, (acc + sc[hh] * p.bk[o]) * p.scale);
     atomicAdd(p.dbk + o, sc[hh] * qo);
   }
 }
@@ -650,7 +650,7 @@ extern "C" int simvgb_head_xattn(const simvgb_head_xattn_args* a, int backward, 
   SIMVGB_CHECK(a->E == 256 && a->H == 8, "simvgb_head_xattn: E = 256, H = 8 (got %d, %d)", a->E, a->H);
   SIMVGB_CHECK(a->B >= 1 && a->nq >= 1 && a->N >= 1, "simvgb_head_xattn: bad shape");
   XAttn p{a->q, a->kin, a->val, a->Wk, a->bk, a->Wv, a->bv, a->drop_u, a->dctx, a->P, a->z, a->kpm, a->ctx, a->P, a->z, a->psum,
-          a->dq, a->dkin, a->dval, a->dWk, a->dbk, a->dWv, a->dbv, a->B, a->nq, a->N, a->E, a->H, a->drop_p};
+          a->dq, a->dkin, a->dval, a->dWk, a->dbk, a->dWv, a->dbv, a->B, a->nq, a->N, a->E, a->H, a->drop_p, a->scale};
   const int rows = a->B * a->nq;
   if (!backward) {
     SIMVGB_CHECK(a->ctx && a->P && a->z && a->psum, "simvgb_head_xattn: forward needs ctx, P, z, psum");

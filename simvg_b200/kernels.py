@@ -458,7 +458,7 @@ class HeadXAttnArgs(ctypes.Structure):
                 ("kpm", L.c_vp), ("drop_u", L.c_vp), ("ctx", L.c_vp), ("P", L.c_vp), ("z", L.c_vp), ("psum", L.c_vp),
                 ("dctx", L.c_vp), ("dq", L.c_vp), ("dkin", L.c_vp), ("dval", L.c_vp), ("dWk", L.c_vp), ("dbk", L.c_vp),
                 ("dWv", L.c_vp), ("dbv", L.c_vp),
-                ("B", L.c_int), ("nq", L.c_int), ("N", L.c_int), ("E", L.c_int), ("H", L.c_int), ("drop_p", L.c_f32)]
+                ("B", L.c_int), ("nq", L.c_int), ("N", L.c_int), ("E", L.c_int), ("H", L.c_int), ("drop_p", L.c_f32), ("scale", L.c_f32)]
 
 
 def _f32c(t):
@@ -560,7 +560,7 @@ def _xattn_args(q, kin, val, Wk, bk, Wv, bv, B, nq, N, kpm, drop_u, drop_p):
     a = HeadXAttnArgs()
     a.q, a.kin, a.val = _p(_f32c(q)), _p(_f32c(kin)), _p(_f32c(val))
     a.Wk, a.bk, a.Wv, a.bv = _p(_f32c(Wk)), _p(_f32c(bk)), _p(_f32c(Wv)), _p(_f32c(bv))
-    a.kpm, a.drop_u, a.B, a.nq, a.N, a.E, a.H, a.drop_p = _p(kpm), _p(drop_u), B, nq, N, 256, 8, drop_p
+    a.kpm, a.drop_u, a.B, a.nq, a.N, a.E, a.H, a.drop_p, a.scale = _p(kpm), _p(drop_u), B, nq, N, 256, 8, drop_p, 32 ** -0.5
     return a
 
 

@@ -149,6 +149,7 @@ class DetrTransformerDecoder(nn.Module):
         self.return_intermediate = return_intermediate
         self.embed_dim = embed_dim
         self.post_norm_layer = nn.LayerNorm(embed_dim) if post_norm else None
+        self.use_native = True   # CUDA tensors run on the fused head kernels (native.py); False = op-by-op path (tests' reference)
 
     def forward(self, query, key, value, query_pos=None, key_pos=None, key_padding_mask=None):
         """Batch-first tensors.  Returns [num_layers | 1, B, nq, E]  (transformer.py:134-186: the shared post-norm is
@@ -156,6 +157,10 @@ class DetrTransformerDecoder(nn.Module):
         inter = []
         # key + key_pos is the same for every layer (the memory is not updated by a decoder): form it once
         cross_k_in = key if key_pos is None else key + key_pos
+        if query.is_cuda and self.use_native and query_pos is not None:
+            from . import native
+            if native.supported(self, query, cross_k_in):
+                return native.decoder_stack(self, query, cross_k_in, value, query_pos, key_padding_mask)
         for layer in self.layers:
             query = layer(query, key, value, query_pos, key_pos, key_padding_mask, cross_k_in=cross_k_in)
             if self.return_intermediate:

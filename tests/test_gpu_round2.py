@@ -255,3 +255,150 @@ def test_nq10_matcher_on_device_equals_scipy_path(lib):
             [{k: v.cuda() for k, v in t.items()} for t in targets])
     for (wq, wt), (gq, gt) in zip(want, got):
         assert gq.is_cuda and wq.tolist() == gq.cpu().tolist() and wt.tolist() == gt.cpu().tolist()
+
+
+# ------------------------------------------------------------------------------------------------ native head kernels
+def _mr(x, ref):
+    return ((x.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-30)).item()
+
+
+def test_head_linear_kernels_match_torch(lib):
+    """simvgb_head_lin_fwd / _bwd: position add on the first n_split outputs, bias, ReLU, dropout from given uniforms, split-K."""
+    from simvg_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for R, N, Kd, n_split, relu, p in ((64, 768, 256, 512, False, 0.0), (70, 2048, 256, 0, True, 0.1), (640, 256, 256, 256, False, 0.0),
+                                       (5, 2, 256, 0, False, 0.0)):
+        x = torch.randn(R, Kd, device=DEV, generator=g).requires_grad_(True)
+        x2 = torch.randn(R, Kd, device=DEV, generator=g).requires_grad_(True) if n_split else None
+        W = (torch.randn(N, Kd, device=DEV, generator=g) * 0.1).requires_grad_(True)
+        b = torch.randn(N, device=DEV, generator=g).requires_grad_(True)
+        u = torch.rand(R, N, device=DEV, generator=g) if p > 0 else None
+        y = K.head_lin_fwd(x.detach(), W.detach(), b.detach(), x2=None if x2 is None else x2.detach(), n_split=n_split, relu=relu,
+                           drop_u=u, drop_p=p)
+        xin = x.unsqueeze(1) if x2 is None else None
+        if x2 is None:
+            ref = torch.nn.functional.linear(x, W, b)
+        else:
+            ref = torch.cat([torch.nn.functional.linear(x + x2, W[:n_split], b[:n_split]),
+                             torch.nn.functional.linear(x, W[n_split:], b[n_split:])], 1)
+        if relu:
+            ref = ref.relu()
+        if u is not None:
+            ref = ref * (u >= p).float() / (1 - p)
+        assert _mr(y, ref) < 1e-5, (R, N, Kd)
+        dy = torch.randn(R, N, device=DEV, generator=g)
+        ref.backward(dy)
+        dx, dx2 = torch.zeros(R, Kd, device=DEV), torch.zeros(R, Kd, device=DEV)
+        dW, db = torch.zeros(N, Kd, device=DEV), torch.zeros(N, device=DEV)
+        K.head_lin_bwd(dy, x.detach(), W.detach(), y=y, x2=None if x2 is None else x2.detach(), n_split=n_split, relu=relu, drop_u=u,
+                       drop_p=p, dx=dx, dx2=None if x2 is None else dx2, dW=dW, db=db)
+        assert _mr(dx, x.grad) < 1e-4 and _mr(dW, W.grad) < 1e-4 and _mr(db, b.grad) < 1e-4, (R, N, Kd)
+        if x2 is not None:
+            assert _mr(dx2, x2.grad) < 1e-4
+    # split-K forward (FFN second layer): zeroed output, bias from split 0
+    x, W, b = torch.randn(64, 2048, device=DEV, generator=g), torch.randn(256, 2048, device=DEV, generator=g) * 0.05, torch.randn(256, device=DEV, generator=g)
+    assert _mr(K.head_lin_fwd(x, W, b, k_splits=8), torch.nn.functional.linear(x, W, b)) < 1e-5
+
+
+def test_head_lnres_and_small_attention_match_torch(lib):
+    from simvg_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(2)
+    R, C, p = 70, 256, 0.1
+    a = torch.randn(R, C, device=DEV, generator=g).requires_grad_(True)
+    b = torch.randn(R, C, device=DEV, generator=g).requires_grad_(True)
+    gm, bt = torch.randn(C, device=DEV, generator=g).requires_grad_(True), torch.randn(C, device=DEV, generator=g).requires_grad_(True)
+    u = torch.rand(R, C, device=DEV, generator=g)
+    mask = (u >= p).float() / (1 - p)
+    ref = torch.nn.functional.layer_norm(a + b * mask, (C,), gm, bt, 1e-5)
+    y, mean, rstd = K.head_lnres_fwd(a.detach(), b.detach(), gm.detach(), bt.detach(), drop_u=u, drop_p=p)
+    assert _mr(y, ref) < 1e-5
+    dy = torch.randn(R, C, device=DEV, generator=g)
+    ref.backward(dy)
+    da, db, dg, dbt = (torch.zeros_like(t) for t in (a, b, gm, bt))
+    K.head_lnres_bwd(dy, a.detach(), b.detach(), gm.detach(), mean, rstd, dg, dbt, da=da, db=db, drop_u=u, drop_p=p)
+    assert _mr(da, a.grad) < 1e-4 and _mr(db, b.grad) < 1e-4 and _mr(dg, gm.grad) < 1e-4 and _mr(dbt, bt.grad) < 1e-4
+    # few-keys attention: packed q|k|v rows (self-attention, nq = nk = 10) and separate projections with a key padding mask (nk = 20)
+    B, H, E = 5, 8, 256
+    for nq, nk, packed in ((10, 10, True), (1, 1, True), (3, 20, False)):
+        if packed:
+            qkv = torch.randn(B * nq, 3 * E, device=DEV, generator=g).requires_grad_(True)
+            q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
+            kpm = None
+        else:
+            q = torch.randn(B * nq, E, device=DEV, generator=g).requires_grad_(True)
+            k = torch.randn(B * nk, E, device=DEV, generator=g).requires_grad_(True)
+            v = torch.randn(B * nk, E, device=DEV, generator=g).requires_grad_(True)
+            kpm = torch.zeros(B, nk, dtype=torch.uint8, device=DEV)
+            kpm[1, 12:] = 1
+            kpm[3, 5:] = 1
+        u = torch.rand(B, H, nq, nk, device=DEV, generator=g)
+        scale = 32 ** -0.5
+        qh = q.reshape(B, nq, H, 32).transpose(1, 2)
+        kh = k.reshape(B, nk, H, 32).transpose(1, 2)
+        vh = v.reshape(B, nk, H, 32).transpose(1, 2)
+        sc = (qh @ kh.transpose(-1, -2)) * scale
+        if kpm is not None:
+            sc = sc.masked_fill(kpm.bool()[:, None, None, :], float("-inf"))
+        pr = sc.softmax(-1)
+        ref = ((pr * (u >= p).float() / (1 - p)) @ vh).transpose(1, 2).reshape(B * nq, E)
+        ctx, P = K.head_attn_small_fwd(q.detach(), k.detach(), v.detach(), B, nq, nk, H, scale, kpm=kpm, drop_u=u, drop_p=p)
+        assert _mr(ctx, ref) < 1e-5 and _mr(P, pr) < 1e-5, (nq, nk)
+        dctx = torch.randn(B * nq, E, device=DEV, generator=g)
+        ref.backward(dctx)
+        if packed:
+            dqkv = torch.zeros_like(qkv)
+            K.head_attn_small_bwd(dctx, q.detach(), k.detach(), v.detach(), P, dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:], B, nq, nk, H,
+                                  scale, drop_u=u, drop_p=p)
+            assert _mr(dqkv, qkv.grad) < 1e-4, (nq, nk)
+        else:
+            dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+            K.head_attn_small_bwd(dctx, q.detach(), k.detach(), v.detach(), P, dq, dk, dv, B, nq, nk, H, scale, drop_u=u, drop_p=p)
+            assert _mr(dq, q.grad) < 1e-4 and _mr(dk, k.grad) < 1e-4 and _mr(dv, v.grad) < 1e-4, (nq, nk)
+
+
+@pytest.mark.parametrize("nq,N,masked", [(1, 400, False), (10, 100, True), (1, 20, True), (4, 20, False)])
+def test_native_decoder_stack_matches_op_by_op_path(lib, nq, N, masked):
+    """DetrTransformerDecoder on the fused head kernels (one autograd node) against its own op-by-op PyTorch path (the
+    implementation the CPU tests pin to the oracle): stacked outputs, input gradients and EVERY parameter gradient — object-token
+    decoder geometry (absorbed cross-attention over N > 32 keys) and text-guided query generation geometry (N = 20 keys)."""
+    from simvg_b200.models.heads.tgqs_kd_detr_head.transformer import DetrTransformerDecoder
+    torch.manual_seed(3)
+    B, E = 4, 256
+    dec = DetrTransformerDecoder(embed_dim=E, num_heads=8, attn_dropout=0.1, feedforward_dim=2048 if N > 32 else 512, ffn_dropout=0.1,
+                                 num_layers=3, return_intermediate=N > 32, post_norm=True).cuda().eval()
+    for p_ in dec.parameters():
+        if p_.dim() > 1:
+            torch.nn.init.xavier_uniform_(p_)
+        else:
+            torch.nn.init.normal_(p_, std=0.2)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    mk = lambda *s: torch.randn(*s, device=DEV, generator=g)  # noqa: E731
+    query, qpos, key, kpos = mk(B, nq, E) * 0.0, mk(B, nq, E), mk(B, N, E), mk(B, N, E)
+    kpm = None
+    if masked:
+        kpm = torch.zeros(B, N, dtype=torch.bool, device=DEV)
+        kpm[0, N // 2:] = True
+        kpm[2, 3:] = True
+    res = {}
+    for native in (False, True):
+        dec.use_native = native
+        dec.zero_grad(set_to_none=True)
+        q_, qp_, k_ = query.clone().requires_grad_(True), qpos.clone().requires_grad_(True), key.clone().requires_grad_(True)
+        out = dec(q_, k_, k_, query_pos=qp_, key_pos=kpos, key_padding_mask=kpm)
+        w = torch.randn(out.shape, device=DEV, generator=torch.Generator(device="cuda").manual_seed(5))
+        (out * w).sum().backward()
+        res[native] = (out.detach(), q_.grad, qp_.grad, k_.grad, {n: p_.grad.clone() for n, p_ in dec.named_parameters()})
+    (o0, dq0, dp0, dk0, g0), (o1, dq1, dp1, dk1, g1) = res[False], res[True]
+    assert o0.shape == o1.shape and _mr(o1, o0) < 2e-5
+    assert _mr(dq1, dq0) < 2e-4 and _mr(dp1, dp0) < 2e-4 and _mr(dk1, dk0) < 2e-4
+    for n in g0:
+        if g0[n].abs().max() < 1e-9:     # e.g. the self-attention q / k projections when nq = 1 (softmax over one key)
+            assert g1[n].abs().max() < 1e-6, n
+            continue
+        assert _mr(g1[n], g0[n]) < 5e-4, (n, _mr(g1[n], g0[n]))
+    # training mode (dropout on): finite outputs and gradients
+    dec.use_native = True
+    dec.train()
+    out = dec(query.clone().requires_grad_(True), key, key, query_pos=qpos, key_pos=kpos, key_padding_mask=kpm)
+    out.sum().backward()
+    assert torch.isfinite(out).all() and all(torch.isfinite(p_.grad).all() for p_ in dec.parameters())
