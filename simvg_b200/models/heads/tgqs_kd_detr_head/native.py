@@ -64,7 +64,9 @@ def _layer_params(layer):
 
 
 def _ffn_splits(F):
-    return max(1, min(16, F // 256))
+    """Split-K factor of the second FFN linear (K = F).  1: the forward stays deterministic (no atomics); at R <= 640 rows the
+    unsplit product is ~6 us on 16 CTAs, which the step graph hides behind nothing but is still ~0.1 % of the step."""
+    return 1
 
 
 def stack_forward(dec, query, qpos, kin, val, kpm, training):
@@ -97,9 +99,11 @@ def stack_forward(dec, query, qpos, kin, val, kpm, training):
         off = li * sum(sizes) + sum(sizes[:which])
         return U[off:off + sizes[which]]
 
-    ar = _Arena()
-    f_idx = [ar.want(R, E) for _ in range(nl)]          # split-K outputs must start at zero
-    f_bufs = ar.build(dev)
+    f_bufs = None
+    if _ffn_splits(F) > 1:                               # split-K outputs must start at zero
+        ar = _Arena()
+        f_idx = [ar.want(R, E) for _ in range(nl)]
+        f_bufs = ar.build(dev)
     saved, outs = [], []
     post = dec.post_norm_layer
     for li, layer in enumerate(dec.layers):
@@ -128,7 +132,7 @@ def stack_forward(dec, query, qpos, kin, val, kpm, training):
         s["x2"], s["m1"], s["r1"] = K.head_lnres_fwd(s["x1"], s["a2"], P["n1w"], P["n1b"])
         # ---- FFN
         s["h"] = K.head_lin_fwd(s["x2"], P["w1"], P["b1"], relu=True, drop_u=u_of(li, 2), drop_p=p_ffn)
-        s["f"] = K.head_lin_fwd(s["h"], P["w2"], P["b2"], k_splits=_ffn_splits(F), out=f_bufs[f_idx[li]])
+        s["f"] = K.head_lin_fwd(s["h"], P["w2"], P["b2"], k_splits=_ffn_splits(F), out=None if f_bufs is None else f_bufs[f_idx[li]])
         s["x3"], s["m2"], s["r2"] = K.head_lnres_fwd(s["x2"], s["f"], P["n2w"], P["n2b"], drop_u=u_of(li, 3), drop_p=p_ffn)
         x = s["x3"]
         if dec.return_intermediate or li == nl - 1:
@@ -247,3 +251,37 @@ def supported(dec, query, kin):
     layer = dec.layers[0]
     return (E == 256 and layer.attentions[0].num_heads == 8 and query.shape[1] <= 32 and
             layer.ffns[0].layers[0][0].weight.shape[0] % 32 == 0)
+
+
+# ------------------------------------------------------------------------------------------------ nn.Linear / MLP on few rows
+class _LinearFn(torch.autograd.Function):
+    """y = relu?(x W^T + b) on simvgb_head_lin_fwd / _bwd (fp32).  dW / db are accumulated into the parameters' .grad in place."""
+
+    @staticmethod
+    def forward(ctx, x2d, lin, relu, anchor):
+        y = K.head_lin_fwd(x2d, lin.weight, lin.bias, relu=relu)
+        ctx.lin, ctx.relu = lin, relu
+        ctx.save_for_backward(x2d, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, y = ctx.saved_tensors
+        lin = ctx.lin
+        dx = torch.zeros_like(x2d) if ctx.needs_input_grad[0] else None
+        with torch.no_grad():
+            K.head_lin_bwd(dy.contiguous().float(), x2d, lin.weight, y=y, relu=ctx.relu, dx=dx,
+                           dW=_grad(lin.weight) if lin.weight.requires_grad else None,
+                           db=_grad(lin.bias) if (lin.bias is not None and lin.bias.requires_grad) else None)
+        return dx, None, None, torch.zeros(1, device=dy.device)
+
+
+def linear(lin, x, relu=False):
+    """nn.Linear `lin` (+ optional ReLU) applied to x [..., K] on the native head kernels (CUDA fp32 tensors)."""
+    lead = x.shape[:-1]
+    x2d = x.reshape(-1, x.shape[-1]).contiguous().float()
+    if torch.is_grad_enabled() and (x2d.requires_grad or lin.weight.requires_grad):
+        y = _LinearFn.apply(x2d, lin, relu, torch.zeros(1, device=x.device, requires_grad=True))
+    else:
+        y = K.head_lin_fwd(x2d, lin.weight, lin.bias, relu=relu)
+    return y.view(*lead, lin.weight.shape[0])

@@ -197,6 +197,14 @@ class TextGuidedQuerySelectKDDETRHead(nn.Module):
         return (vals * wv).sum()
 
     # ------------------------------------------------------------------------------------------ forward
+    @staticmethod
+    def _lin(mod, x):
+        """nn.Linear on the native fp32 head kernel for CUDA tensors (few rows: latency-bound), plain module call otherwise."""
+        if x.is_cuda and x.dtype == torch.float32:
+            from . import native
+            return native.linear(mod, x)
+        return mod(x)
+
     def x_mask_pos_enc(self, B, hw, img_metas, device):
         """Padding mask + 2-D sine positions (tgqs_kd_detr_head.py:322-338), cached per (batch geometry)."""
         try:
@@ -224,8 +232,8 @@ class TextGuidedQuerySelectKDDETRHead(nn.Module):
             mem_in = x_mm.permute(0, 2, 3, 1).reshape(B * h * w, C)
             memory = ops.linear(mem_in, self.input_proj.weight.view(E, C), self.input_proj.bias).view(B, h * w, E)
             img_masks, pos_embed = self.x_mask_pos_enc(B, (h, w), img_metas, x_mm.device)
-        text_feat = self.input_text_proj(text_feat)
-        cls_feat = self.input_cls_proj(cls_feat).unsqueeze(1)
+        text_feat = self._lin(self.input_text_proj, text_feat)
+        cls_feat = self._lin(self.input_cls_proj, cls_feat).unsqueeze(1)
         cls_feat = cls_feat.repeat((1, nq, 1))
         if self.text_guided_query_generation:
             # `~text_mask` on the loader's int64 mask is a bitwise NOT -> integer row gather (rows -1 / -2), Appendix C.1
@@ -250,7 +258,7 @@ class TextGuidedQuerySelectKDDETRHead(nn.Module):
             cls_feat = self.mlp(cls_feat)
             if self.num_token_mlp_layers == 0:
                 cls_feat = cls_feat.unsqueeze(0)
-            cls_tok = self.class_embed_token(cls_feat)
+            cls_tok = self._lin(self.class_embed_token, cls_feat)
             coord_tok = self.bbox_embed_token(cls_feat).sigmoid()
             token_branch_output = {"pred_logits": cls_tok[-1], "pred_boxes": coord_tok[-1]}
         if token_only:   # the reference's `only_token` branch (tgqs_kd_detr_head.py:434-441)
@@ -259,7 +267,7 @@ class TextGuidedQuerySelectKDDETRHead(nn.Module):
                     "outputs_class_token_branch": cls_tok, "outputs_coord_token_branch": coord_tok,
                     "token_features": cls_feat, "decoder_features": None}
         hidden_states = self.transformer(memory, img_masks, query_embed, pos_embed)
-        cls_dec = self.class_embed_decoder(hidden_states)
+        cls_dec = self._lin(self.class_embed_decoder, hidden_states)
         coord_dec = self.bbox_embed_decoder(hidden_states).sigmoid()
         decoder_branch_output = {"pred_logits": cls_dec[-1], "pred_boxes": coord_dec[-1]}
         return {"token_branch_output": token_branch_output, "decoder_branch_output": decoder_branch_output,

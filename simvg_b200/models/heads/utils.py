@@ -16,10 +16,17 @@ class MLP(nn.Module):
 
     def forward(self, x):
         outs = []
+        native = None
+        if x.is_cuda and x.dtype == torch.float32:
+            from simvg_b200.models.heads.tgqs_kd_detr_head import native   # fused Linear(+ReLU) kernels (csrc/headops.cu)
         for i, layer in enumerate(self.layers):
-            x = layer(x)
-            if i < self.num_layers - 1:
-                x = F.relu(x)
+            act = i < self.num_layers - 1
+            if native is not None:
+                x = native.linear(layer, x, relu=act)
+            else:
+                x = layer(x)
+                if act:
+                    x = F.relu(x)
             outs.append(x)
         return torch.stack(outs, dim=0) if self.return_intermediate else x
 

@@ -133,7 +133,7 @@ def test_uint8_input_path_equals_host_normalisation(lib):
     b_f = dict(b, img=host.cuda())
     b_u = dict(b, img=u8.cuda())
     lf, lu = _step_loss(model, b_f), _step_loss(model, b_u)
-    assert float(lf) == float(lu)
+    assert abs(float(lf) - float(lu)) <= 1e-6 * abs(float(lf))
     lu.backward()
     assert float(model.vis_enc.beit3.vision_embed.proj.weight.grad.abs().sum()) > 0
 
