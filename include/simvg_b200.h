@@ -280,7 +280,11 @@ typedef struct simvgb_head_xattn_args {
   int32_t B, nq, N, E, H;
   float drop_p;
   float scale;           /* head_dim^-0.5, applied to q inside */
+  float* ws;             /* scratch, >= simvgb_head_xattn_ws_floats(B, nq, N, backward) floats, 16-byte aligned */
+  long long ws_floats;
 } simvgb_head_xattn_args;
+/* Scratch the call needs (absorbed vectors, per-key-chunk partial sums, the backward's score gradients), in floats. */
+long long simvgb_head_xattn_ws_floats(int B, int nq, int N, int backward);
 int simvgb_head_xattn(const simvgb_head_xattn_args* args, int backward, void* stream);
 
 /* Hungarian matching on the device (detrex HungarianMatcher + scipy.optimize.linear_sum_assignment; called from

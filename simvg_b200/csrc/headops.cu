@@ -352,214 +352,313 @@ __global__ void __launch_bounds__(128) attn_small_bwd_kernel(const AttnSmall p) 
 //     u[h]   = Wk_h^T q_h            c[h] = q_h . bk_h               (q = scale * the projected query)
 //     s[h,n] = u[h] . kin[b,n] + c[h]         p = softmax_n(s)  (key padding mask),  pd = dropout(p)
 //     z[h]   = sum_n pd[h,n] val[b,n]         ctx_h = Wv_h z[h] + bv_h sum_n pd[h,n]
-// One CTA (256 threads = 8 warps, warp w = head w) per (b, i): the memory rows of sample b are read once per pass for all heads.
-struct XAttn {
-  const float *q, *kin, *val, *Wk, *bk, *Wv, *bv, *drop_u, *dctx, *P_in, *z_in;
-  const unsigned char* kpm;    // [B, N] or null
-  float *ctx, *P, *z, *psum;   // P [R, H, N] (pre-dropout), z [R, H, E], psum [R, H]
-  float *dq, *dkin, *dval, *dWk, *dbk, *dWv, *dbv;
-  int B, nq, N, E, H;
-  float drop_p, scale;
-};
+// There are only B * nq * H "virtual queries", so the parallelism has to come from the keys: every pass over the memory is a grid
+// over (key tile, sample); the per-row steps (absorb, softmax, output projection) are separate small launches.  No atomics
+// anywhere: per-chunk partial sums are written out and reduced by the following launch, so forward and backward are
+// deterministic.
+constexpr int XE = 256, XH = 8, XK = 32;     // model width, heads, keys per tile
+constexpr int XTS = XE + 1;                  // padded smem row of a key tile
 
-__global__ void __launch_bounds__(256) xattn_fwd_kernel(const XAttn p) {
-  extern __shared__ float xs[];
-  float* u = xs;                       // [H][E]
-  float* zs = xs + p.H * p.E;          // [H][E]
-  float* red = zs + p.H * p.E;         // [H][2]: max, sum
+// u[r,h,:] = alpha * W_h^T x_h,  c[r,h] = alpha * x_h . b_h       (forward: x = q, W = Wk, alpha = scale;  backward: x = dctx, W = Wv)
+__global__ void __launch_bounds__(256) xattn_absorb_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                           const float* __restrict__ bias, float* __restrict__ u,
+                                                           float* __restrict__ c, float alpha) {
+  __shared__ float xs[XE];
+  const int r = blockIdx.x, e = threadIdx.x;
+  xs[e] = x[(long long)r * XE + e] * alpha;
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < XH; ++h) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < 32; ++d) acc = fmaf(xs[h * 32 + d], W[(long long)(h * 32 + d) * XE + e], acc);
+    u[((long long)r * XH + h) * XE + e] = acc;
+  }
+  const int warp = e >> 5, lane = e & 31;
+  const float cc = warp_sum(xs[warp * 32 + lane] * bias[warp * 32 + lane]);
+  if (lane == 0) c[r * XH + warp] = cc;
+}
+
+// out[(b*nq+i)*H + h][n] = vec[b*nq+i, h, :] . mat[b, n, :] + add[b*nq+i, h]     (-inf at masked keys when kpm is given)
+// grid (key tiles, B); warp = head, lane = key of the tile; two queries per pass over the staged tile.
+__global__ void __launch_bounds__(256) xattn_dot_kernel(const float* __restrict__ vec, const float* __restrict__ add,
+                                                        const float* __restrict__ mat, const unsigned char* __restrict__ kpm,
+                                                        float* __restrict__ out, int nq, int N) {
+  extern __shared__ __align__(16) float xsm[];
+  float* tile = xsm;                   // [XK][XTS]
+  float* vs = xsm + XK * XTS;          // [2][XH][XE]
+  const int b = blockIdx.y, n0 = blockIdx.x * XK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x;          // b * nq + i
-  const int b = row / p.nq;
-  const int E = p.E, H = p.H, N = p.N;
-  const float* q = p.q + (long long)row * E;
-  // u[h][e] = sum_d q[h*32+d] Wk[h*32+d][e]
-  for (int idx = threadIdx.x; idx < H * E; idx += 256) {
-    const int h = idx / E, e = idx % E;
-    float acc = 0.f;
+  for (int idx = threadIdx.x; idx < XK * (XE / 4); idx += 256) {
+    const int k = idx >> 6, e4 = idx & 63;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + k < N) v = *reinterpret_cast<const float4*>(mat + ((long long)b * N + n0 + k) * XE + e4 * 4);
+    float* t = tile + k * XTS + e4 * 4;
+    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+  }
+  const int n = n0 + lane;
+  const bool live = n < N;
+  const bool masked = live && kpm != nullptr && kpm[(long long)b * N + n] != 0;
+  const float* t = tile + lane * XTS;
+  for (int i0 = 0; i0 < nq; i0 += 2) {
+    const int nqi = min(2, nq - i0);
+    __syncthreads();                   // tile staged (first pass) / previous vectors consumed
+    const float4* src = reinterpret_cast<const float4*>(vec + (long long)(b * nq + i0) * XH * XE);
+    for (int idx = threadIdx.x; idx < 2 * XH * XE / 4; idx += 256)
+      reinterpret_cast<float4*>(vs)[idx] = idx < nqi * XH * XE / 4 ? src[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const float* v0 = vs + warp * XE;
+    const float* v1 = vs + XH * XE + warp * XE;
+    float a0 = 0.f, a1 = 0.f;
 #pragma unroll 8
-    for (int d = 0; d < 32; ++d) acc = fmaf(q[h * 32 + d], p.Wk[(long long)(h * 32 + d) * E + e], acc);
-    u[idx] = acc * p.scale;
-    zs[idx] = 0.f;
-  }
-  __syncthreads();
-  const int h = warp;                  // H == 8 == warps
-  float c = 0.f;
-  for (int d = lane; d < 32; d += 32) c += q[h * 32 + d] * p.bk[h * 32 + d];
-  c = warp_sum(c) * p.scale;
-  // pass 1: scores -> P buffer (raw), running max
-  float* Prow = p.P + ((long long)row * H + h) * N;
-  float uh[8];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) uh[t] = u[h * E + lane + 32 * t];     // E == 256: 8 values per lane
-  float mx = -INFINITY;
-  for (int n = 0; n < N; ++n) {
-    const float* kr = p.kin + ((long long)b * N + n) * E;
-    float acc = 0.f;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) acc = fmaf(uh[t], kr[lane + 32 * t], acc);
-    acc = warp_sum(acc) + c;
-    if (p.kpm != nullptr && p.kpm[(long long)b * N + n]) acc = -INFINITY;
-    if (lane == 0) Prow[n] = acc;
-    mx = fmaxf(mx, acc);
-  }
-  __syncwarp();
-  // pass 2: exponentials and sum (lanes over n)
-  float sum = 0.f;
-  for (int n = lane; n < N; n += 32) {
-    const float s = Prow[n];
-    const float e = (s == -INFINITY) ? 0.f : __expf(s - mx);
-    Prow[n] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  const float inv = 1.f / sum;
-  __syncwarp();
-  // pass 3: normalise, dropout, z[h] = sum_n pd val[n]   (lane owns 8 channels)
-  float zacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float ps = 0.f;
-  const float* du = p.drop_u == nullptr ? nullptr : p.drop_u + ((long long)row * H + h) * N;
-  for (int n0 = 0; n0 < N; n0 += 32) {
-    const int n = n0 + lane;
-    float pr = 0.f, pd = 0.f;
-    if (n < N) {
-      pr = Prow[n] * inv;
-      Prow[n] = pr;
-      pd = pr * drop_scale(du, n, p.drop_p);
+    for (int e = 0; e < XE; e += 4) {
+      const float4 x0 = *reinterpret_cast<const float4*>(v0 + e);
+      const float4 x1 = *reinterpret_cast<const float4*>(v1 + e);
+      const float t0 = t[e], t1 = t[e + 1], t2 = t[e + 2], t3 = t[e + 3];
+      a0 = fmaf(x0.x, t0, a0); a0 = fmaf(x0.y, t1, a0); a0 = fmaf(x0.z, t2, a0); a0 = fmaf(x0.w, t3, a0);
+      a1 = fmaf(x1.x, t0, a1); a1 = fmaf(x1.y, t1, a1); a1 = fmaf(x1.z, t2, a1); a1 = fmaf(x1.w, t3, a1);
     }
-    ps += pd;
-    const int cnt = min(32, N - n0);
-    for (int j = 0; j < cnt; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, pd, j);
-      if (pj == 0.f) continue;
-      const float* vr = p.val + ((long long)b * N + n0 + j) * E;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) zacc[t] = fmaf(pj, vr[lane + 32 * t], zacc[t]);
+    if (live) {
+      const long long row0 = (long long)(b * nq + i0) * XH + warp;
+      out[row0 * N + n] = masked ? -INFINITY : a0 + add[row0];
+      if (nqi > 1) out[(row0 + XH) * N + n] = masked ? -INFINITY : a1 + add[row0 + XH];
     }
-  }
-  ps = warp_sum(ps);
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    zs[h * E + lane + 32 * t] = zacc[t];
-    p.z[((long long)row * H + h) * E + lane + 32 * t] = zacc[t];
-  }
-  if (lane == 0) { p.psum[(long long)row * H + h] = ps; red[h] = ps; }
-  __syncthreads();
-  // ctx[h*32 + d] = Wv[h*32+d] . z[h] + bv[h*32+d] * psum[h]     (one output per thread: 256 threads = E outputs)
-  {
-    const int o = threadIdx.x, hh = o / 32;
-    const float* wr = p.Wv + (long long)o * E;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int e = 0; e < 256; ++e) acc = fmaf(wr[e], zs[hh * E + e], acc);
-    p.ctx[(long long)row * E + o] = acc + p.bv[o] * red[hh];
   }
 }
 
-// Backward of the above; one CTA per (b, i), warp = head.  dkin / dval accumulate with atomics (queries of a sample share them).
-__global__ void __launch_bounds__(256) xattn_bwd_kernel(const XAttn p) {
-  extern __shared__ float xs[];
-  float* u = xs;                       // [H][E]
-  float* dz = xs + p.H * p.E;          // [H][E]
-  float* du_s = dz + p.H * p.E;        // [H][E]  gradient w.r.t. u
-  float* sc = du_s + p.H * p.E;        // [H][2]: dpsum, dc
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x;
-  const int b = row / p.nq;
-  const int E = p.E, H = p.H, N = p.N;
-  const float* q = p.q + (long long)row * E;
-  const float* dctx = p.dctx + (long long)row * E;
-  // recompute u; dz[h][e] = sum_d dctx[h*32+d] Wv[h*32+d][e]
-  for (int idx = threadIdx.x; idx < H * E; idx += 256) {
-    const int h = idx / E, e = idx % E;
-    float a = 0.f, g = 0.f;
-#pragma unroll 8
-    for (int d = 0; d < 32; ++d) {
-      a = fmaf(q[h * 32 + d], p.Wk[(long long)(h * 32 + d) * E + e], a);
-      g = fmaf(dctx[h * 32 + d], p.Wv[(long long)(h * 32 + d) * E + e], g);
-    }
-    u[idx] = a * p.scale;
-    dz[idx] = g;
-    du_s[idx] = 0.f;
+// In place: scores -> probabilities; psum[row] = sum_n p[n] * dropmask[n].  One warp per (b, i, h) row.
+__global__ void __launch_bounds__(128) xattn_softmax_kernel(float* __restrict__ P, const float* __restrict__ drop_u,
+                                                            float* __restrict__ psum, int rows, int N, float drop_p) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* pr = P + (long long)row * N;
+  const float* du = drop_u == nullptr ? nullptr : drop_u + (long long)row * N;
+  float mx = -INFINITY;
+  for (int n = lane; n < N; n += 32) mx = fmaxf(mx, pr[n]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int n = lane; n < N; n += 32) {
+    const float sc = pr[n];
+    const float ex = (sc == -INFINITY) ? 0.f : __expf(sc - mx);
+    pr[n] = ex;
+    sum += ex;
   }
-  // dWv[o][e] += dctx[o] z[h(o)][e];  dbv[o] += dctx[o] psum[h(o)]
-  {
-    const int o = threadIdx.x, hh = o / 32;
-    const float g = dctx[o];
-    const float* zr = p.z_in + ((long long)row * H + hh) * E;
-    float* wr = p.dWv + (long long)o * E;
-    for (int e = 0; e < E; ++e) atomicAdd(wr + e, g * zr[e]);
-    atomicAdd(p.dbv + o, g * p.psum[(long long)row * H + hh]);
+  const float inv = 1.f / warp_sum(sum);
+  float ps = 0.f;
+  for (int n = lane; n < N; n += 32) {
+    const float v = pr[n] * inv;
+    pr[n] = v;
+    ps += v * drop_scale(du, n, drop_p);
   }
-  __syncthreads();
-  const int h = warp;
-  // dpsum[h] = sum_d dctx[h*32+d] bv[h*32+d]
-  float dps = dctx[h * 32 + lane] * p.bv[h * 32 + lane];
-  dps = warp_sum(dps);
-  const float* Prow = p.P_in + ((long long)row * H + h) * N;
-  const float* dun = p.drop_u == nullptr ? nullptr : p.drop_u + ((long long)row * H + h) * N;
-  float dzh[8], uh[8];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) { dzh[t] = dz[h * E + lane + 32 * t]; uh[t] = u[h * E + lane + 32 * t]; }
-  // pass A: dpd[n] = dz[h] . val[n] + dpsum;  dp = dpd * mask;  dot = sum_n dp[n] p[n];  also dval[n] += pd[n] dz[h]
+  ps = warp_sum(ps);
+  if (lane == 0) psum[row] = ps;
+}
+
+// In place: dpd -> ds.  dp = dpd * dropmask;  dot = sum_n dp p;  ds = p (dp - dot);  dc[row] = sum_n ds.
+__global__ void __launch_bounds__(128) xattn_softmax_bwd_kernel(float* __restrict__ dP, const float* __restrict__ P,
+                                                                const float* __restrict__ drop_u, float* __restrict__ dc,
+                                                                int rows, int N, float drop_p) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* dr = dP + (long long)row * N;
+  const float* pr = P + (long long)row * N;
+  const float* du = drop_u == nullptr ? nullptr : drop_u + (long long)row * N;
   float dot = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float pr = Prow[n];
-    if (pr == 0.f) continue;           // masked keys (and exact zeros) contribute nothing
-    const float m = drop_scale(dun, n, p.drop_p);
-    const float* vr = p.val + ((long long)b * N + n) * E;
-    float acc = 0.f;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) acc = fmaf(dzh[t], vr[lane + 32 * t], acc);
-    acc = warp_sum(acc) + dps;
-    dot += acc * m * pr;
-    if (m != 0.f) {
-      float* dvr = p.dval + ((long long)b * N + n) * E;
-      const float pd = pr * m;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) atomicAdd(dvr + lane + 32 * t, pd * dzh[t]);
-    }
+  for (int n = lane; n < N; n += 32) {
+    const float dp = dr[n] * drop_scale(du, n, drop_p);
+    dr[n] = dp;
+    dot = fmaf(dp, pr[n], dot);
   }
-  // pass B: ds[n] = p[n] (dp[n] - dot);  dkin[n] += ds[n] u[h];  du[h] += ds[n] kin[n];  dc += ds[n]
-  float duh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float dc = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float pr = Prow[n];
-    if (pr == 0.f) continue;
-    const float m = drop_scale(dun, n, p.drop_p);
-    const float* vr = p.val + ((long long)b * N + n) * E;
-    float acc = 0.f;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) acc = fmaf(dzh[t], vr[lane + 32 * t], acc);
-    acc = warp_sum(acc) + dps;
-    const float ds = pr * (acc * m - dot);
-    dc += ds;
-    const float* kr = p.kin + ((long long)b * N + n) * E;
-    float* dkr = p.dkin + ((long long)b * N + n) * E;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      duh[t] = fmaf(ds, kr[lane + 32 * t], duh[t]);
-      atomicAdd(dkr + lane + 32 * t, ds * uh[t]);
-    }
+  dot = warp_sum(dot);
+  float dcs = 0.f;
+  for (int n = lane; n < N; n += 32) {
+    const float ds = pr[n] * (dr[n] - dot);
+    dr[n] = ds;
+    dcs += ds;
   }
+  dcs = warp_sum(dcs);
+  if (lane == 0) dc[row] = dcs;
+}
+
+// part[c][row, h, :] = sum_{n in key chunk c} w[row, h, n] * mat[b, n, :],   w = Wt * dropmask (drop_u may be null)
+// grid (chunks, B), thread = channel; four queries (32 weight rows) per pass over the chunk.
+__global__ void __launch_bounds__(256) xattn_wsum_kernel(const float* __restrict__ Wt, const float* __restrict__ drop_u,
+                                                         const float* __restrict__ mat, float* __restrict__ part, int nq, int N,
+                                                         int CL, float drop_p) {
+  __shared__ __align__(16) float wsm[4 * XH][XK];
+  const int b = blockIdx.y, c = blockIdx.x, e = threadIdx.x;
+  const int nlo = c * CL, nhi = min(N, nlo + CL);
+  const long long R = (long long)gridDim.y * nq;
+  for (int i0 = 0; i0 < nq; i0 += 4) {
+    const int rows = min(4, nq - i0) * XH;
+    float acc[4 * XH];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) du_s[h * E + lane + 32 * t] = duh[t];
-  if (lane == 0) sc[h] = dc;
+    for (int ih = 0; ih < 4 * XH; ++ih) acc[ih] = 0.f;
+    for (int n0 = nlo; n0 < nhi; n0 += XK) {
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < rows * XK; idx += 256) {
+        const int ih = idx >> 5, n = n0 + (idx & 31);
+        float w = 0.f;
+        if (n < nhi) {
+          const long long off = ((long long)(b * nq + i0) * XH + ih) * N + n;
+          w = Wt[off] * drop_scale(drop_u, off, drop_p);
+        }
+        wsm[ih][idx & 31] = w;
+      }
+      float v[XK];
+#pragma unroll
+      for (int k = 0; k < XK; ++k) v[k] = (n0 + k < nhi) ? mat[((long long)b * N + n0 + k) * XE + e] : 0.f;
+      __syncthreads();
+#pragma unroll
+      for (int ih = 0; ih < 4 * XH; ++ih) {
+        if (ih < rows) {
+#pragma unroll
+          for (int k = 0; k < XK; k += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&wsm[ih][k]);
+            acc[ih] = fmaf(w4.x, v[k], acc[ih]);
+            acc[ih] = fmaf(w4.y, v[k + 1], acc[ih]);
+            acc[ih] = fmaf(w4.z, v[k + 2], acc[ih]);
+            acc[ih] = fmaf(w4.w, v[k + 3], acc[ih]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int ih = 0; ih < 4 * XH; ++ih)
+      if (ih < rows) part[(((long long)c * R + b * nq + i0) * XH + ih) * XE + e] = acc[ih];
+  }
+}
+
+// z[r,h,:] = sum_c part[c][r,h,:]  (stored);   y[r, o] (+)= alpha * (W[o] . z[r, h(o)] + bias[o] * s[r, h(o)])
+// forward: y = ctx, W = Wv, s = psum;   backward: y = dq (accumulated), W = Wk, s = dc, alpha = scale.
+__global__ void __launch_bounds__(256) xattn_out_kernel(const float* __restrict__ part, int NC, const float* __restrict__ s,
+                                                        const float* __restrict__ W, const float* __restrict__ bias,
+                                                        float* __restrict__ z, float* __restrict__ y, float alpha, int accumulate,
+                                                        int R) {
+  __shared__ float zs[XH * XE];
+  const int r = blockIdx.x, e = threadIdx.x;
+#pragma unroll
+  for (int h = 0; h < XH; ++h) {
+    float a = 0.f;
+    for (int c = 0; c < NC; ++c) a += part[(((long long)c * R + r) * XH + h) * XE + e];
+    zs[h * XE + e] = a;
+    z[((long long)r * XH + h) * XE + e] = a;
+  }
   __syncthreads();
-  // dq[h*32+d] = sum_e du[h][e] Wk[h*32+d][e] + dc[h] bk[h*32+d];  dWk[h*32+d][e] += q[h*32+d] du[h][e];  dbk[h*32+d] += dc[h] q[h*32+d]
-  {
-    const int o = threadIdx.x, hh = o / 32;
-    const float* wr = p.Wk + (long long)o * E;
-    float* dwr = p.dWk + (long long)o * E;
-    const float qo = q[o] * p.scale;
-    float acc = 0.f;
-    for (int e = 0; e < E; ++e) {
-      const float g = du_s[hh * E + e];
-      acc = fmaf(g, wr[e], acc);
-      atomicAdd(dwr + e, qo * g);
-    }
-    atomicAdd(p.dq + (long long)row * E + o, (acc + sc[hh] * p.bk[o]) * p.scale);
-    atomicAdd(p.dbk + o, sc[hh] * qo);
+  const int warp = e >> 5, lane = e & 31;      // warp = head, its 32 outputs one after the other
+  float zr[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) zr[t] = zs[warp * XE + lane + 32 * t];
+  float mine = 0.f;
+  for (int j = 0; j < 32; ++j) {
+    const float* wr = W + (long long)(warp * 32 + j) * XE;
+    float a = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) a = fmaf(wr[lane + 32 * t], zr[t], a);
+    a = warp_sum(a);
+    if (lane == j) mine = a;
   }
+  const int o = warp * 32 + lane;
+  const float v = alpha * (mine + bias[o] * s[r * XH + warp]);
+  float* dst = y + (long long)r * XE + o;
+  *dst = accumulate ? *dst + v : v;
+}
+
+// dkin[b,n,:] += sum_{i,h} ds[i,h,n] u[i,h,:];   dval[b,n,:] += sum_{i,h} pd[i,h,n] dz[i,h,:]      grid (key tiles, B), thread = channel
+__global__ void __launch_bounds__(256) xattn_bwd_kv_kernel(const float* __restrict__ ds, const float* __restrict__ P,
+                                                           const float* __restrict__ drop_u, const float* __restrict__ u,
+                                                           const float* __restrict__ dz, float* __restrict__ dkin,
+                                                           float* __restrict__ dval, int nq, int N, float drop_p) {
+  extern __shared__ __align__(16) float xsm[];
+  const int IH = nq * XH;
+  float* ds_s = xsm;                   // [IH][XK]
+  float* pd_s = xsm + IH * XK;         // [IH][XK]
+  const int b = blockIdx.y, n0 = blockIdx.x * XK, e = threadIdx.x;
+  for (int idx = threadIdx.x; idx < IH * XK; idx += 256) {
+    const int ih = idx >> 5, n = n0 + (idx & 31);
+    float a = 0.f, w = 0.f;
+    if (n < N) {
+      const long long off = ((long long)b * IH + ih) * N + n;
+      a = ds[off];
+      w = P[off] * drop_scale(drop_u, off, drop_p);
+    }
+    ds_s[idx] = a;
+    pd_s[idx] = w;
+  }
+  __syncthreads();
+  float ok[XK], ov[XK];
+#pragma unroll
+  for (int k = 0; k < XK; ++k) { ok[k] = 0.f; ov[k] = 0.f; }
+  for (int ih = 0; ih < IH; ++ih) {
+    const float uu = u[((long long)b * IH + ih) * XE + e];
+    const float zz = dz[((long long)b * IH + ih) * XE + e];
+#pragma unroll
+    for (int k = 0; k < XK; k += 4) {
+      const float4 a4 = *reinterpret_cast<const float4*>(ds_s + ih * XK + k);
+      const float4 w4 = *reinterpret_cast<const float4*>(pd_s + ih * XK + k);
+      ok[k] = fmaf(a4.x, uu, ok[k]); ok[k + 1] = fmaf(a4.y, uu, ok[k + 1]);
+      ok[k + 2] = fmaf(a4.z, uu, ok[k + 2]); ok[k + 3] = fmaf(a4.w, uu, ok[k + 3]);
+      ov[k] = fmaf(w4.x, zz, ov[k]); ov[k + 1] = fmaf(w4.y, zz, ov[k + 1]);
+      ov[k + 2] = fmaf(w4.z, zz, ov[k + 2]); ov[k + 3] = fmaf(w4.w, zz, ov[k + 3]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < XK; ++k) {
+    if (n0 + k < N) {
+      const long long off = ((long long)b * N + n0 + k) * XE + e;
+      dkin[off] += ok[k];
+      dval[off] += ov[k];
+    }
+  }
+}
+
+// dW[o][e] += sum_r alpha a[r,o] z[r,h(o),e];   db[o] += sum_r alpha a[r,o] s[r,h(o)]       grid (8 column tiles, 8 heads)
+__global__ void __launch_bounds__(256) xattn_bwd_w_kernel(const float* __restrict__ a, const float* __restrict__ z,
+                                                          const float* __restrict__ s, float* __restrict__ dW,
+                                                          float* __restrict__ db, float alpha, int R) {
+  __shared__ float as_[32][33], zs_[32][33], ss_[32];
+  const int et = blockIdx.x, h = blockIdx.y;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r0 = 0; r0 < R; r0 += 32) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rr = ty * 4 + j, r = r0 + rr;
+      as_[rr][tx] = r < R ? a[(long long)r * XE + h * 32 + tx] * alpha : 0.f;
+      zs_[rr][tx] = r < R ? z[((long long)r * XH + h) * XE + et * 32 + tx] : 0.f;
+    }
+    if (threadIdx.x < 32) ss_[threadIdx.x] = r0 + threadIdx.x < R ? s[(long long)(r0 + threadIdx.x) * XH + h] : 0.f;
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr) {
+      const float zv = zs_[rr][tx], sv = ss_[rr];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float av = as_[rr][ty * 4 + j];
+        acc[j] = fmaf(av, zv, acc[j]);
+        accb[j] = fmaf(av, sv, accb[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int o = h * 32 + ty * 4 + j;
+    dW[(long long)o * XE + et * 32 + tx] += acc[j];
+    if (et == 0 && tx == 0) db[o] += accb[j];
+  }
+}
+
+struct XPlan { int NC, CL; long long fwd_floats, bwd_floats; };
+static XPlan xattn_plan(int B, int nq, int N) {
+  XPlan pl;
+  const int tiles = (N + XK - 1) / XK;
+  pl.NC = tiles < 8 ? tiles : 8;
+  pl.CL = ((tiles + pl.NC - 1) / pl.NC) * XK;
+  const long long R = (long long)B * nq, RHE = R * XH * XE, RH = R * XH;
+  pl.fwd_floats = RHE + RH + pl.NC * RHE;
+  pl.bwd_floats = RHE + RH + RHE + RH + RH + RH * N + pl.NC * RHE + RHE;
+  return pl;
 }
 
 }  // namespace simvgb
@@ -645,22 +744,51 @@ extern "C" int simvgb_head_attn_small(const simvgb_head_attn_args* a, int backwa
   return 0;
 }
 
+extern "C" long long simvgb_head_xattn_ws_floats(int B, int nq, int N, int backward) {
+  if (B < 1 || nq < 1 || N < 1) return -1;
+  const XPlan pl = xattn_plan(B, nq, N);
+  return backward ? pl.bwd_floats : pl.fwd_floats;
+}
+
 extern "C" int simvgb_head_xattn(const simvgb_head_xattn_args* a, int backward, void* stream) {
   SIMVGB_CHECK(a && a->q && a->kin && a->val && a->Wk && a->bk && a->Wv && a->bv, "simvgb_head_xattn: null pointer");
-  SIMVGB_CHECK(a->E == 256 && a->H == 8, "simvgb_head_xattn: E = 256, H = 8 (got %d, %d)", a->E, a->H);
+  SIMVGB_CHECK(a->E == XE && a->H == XH, "simvgb_head_xattn: E = 256, H = 8 (got %d, %d)", a->E, a->H);
   SIMVGB_CHECK(a->B >= 1 && a->nq >= 1 && a->N >= 1, "simvgb_head_xattn: bad shape");
-  XAttn p{a->q, a->kin, a->val, a->Wk, a->bk, a->Wv, a->bv, a->drop_u, a->dctx, a->P, a->z, a->kpm, a->ctx, a->P, a->z, a->psum,
-          a->dq, a->dkin, a->dval, a->dWk, a->dbk, a->dWv, a->dbv, a->B, a->nq, a->N, a->E, a->H, a->drop_p, a->scale};
-  const int rows = a->B * a->nq;
+  const XPlan pl = xattn_plan(a->B, a->nq, a->N);
+  SIMVGB_CHECK(a->ws != nullptr && a->ws_floats >= (backward ? pl.bwd_floats : pl.fwd_floats),
+               "simvgb_head_xattn: workspace too small (see simvgb_head_xattn_ws_floats)");
+  const int B = a->B, nq = a->nq, N = a->N, R = B * nq;
+  const long long RHE = (long long)R * XH * XE, RH = (long long)R * XH;
+  const dim3 tiles((N + XK - 1) / XK, B), chunks(pl.NC, B);
+  const int dot_smem = (XK * XTS + 2 * XH * XE) * (int)sizeof(float);
+  SIMVGB_CHECK(ensure_dynamic_smem((const void*)xattn_dot_kernel, dot_smem) == 0, "simvgb_head_xattn: shared memory opt-in failed");
+  cudaStream_t st = S(stream);
+  float* w = a->ws;
   if (!backward) {
     SIMVGB_CHECK(a->ctx && a->P && a->z && a->psum, "simvgb_head_xattn: forward needs ctx, P, z, psum");
-    const int smem = (2 * a->H * a->E + 2 * a->H) * sizeof(float);
-    xattn_fwd_kernel<<<rows, 256, smem, S(stream)>>>(p);
+    float *u = w, *c = u + RHE, *part = c + RH;
+    xattn_absorb_kernel<<<R, 256, 0, st>>>(a->q, a->Wk, a->bk, u, c, a->scale);
+    xattn_dot_kernel<<<tiles, 256, dot_smem, st>>>(u, c, a->kin, a->kpm, a->P, nq, N);
+    xattn_softmax_kernel<<<(int)((RH + 3) / 4), 128, 0, st>>>(a->P, a->drop_u, a->psum, (int)RH, N, a->drop_p);
+    xattn_wsum_kernel<<<chunks, 256, 0, st>>>(a->P, a->drop_u, a->val, part, nq, N, pl.CL, a->drop_p);
+    xattn_out_kernel<<<R, 256, 0, st>>>(part, pl.NC, a->psum, a->Wv, a->bv, a->z, a->ctx, 1.f, 0, R);
   } else {
     SIMVGB_CHECK(a->dctx && a->P && a->z && a->psum && a->dq && a->dkin && a->dval && a->dWk && a->dbk && a->dWv && a->dbv,
                  "simvgb_head_xattn: backward needs dctx, P, z, psum and every gradient buffer");
-    const int smem = (3 * a->H * a->E + 2 * a->H) * sizeof(float);
-    xattn_bwd_kernel<<<rows, 256, smem, S(stream)>>>(p);
+    float *u = w, *c = u + RHE, *dz = c + RH, *dps = dz + RHE, *dc = dps + RH, *dP = dc + RH, *part = dP + RH * N, *du = part + pl.NC * RHE;
+    SIMVGB_CHECK(nq <= 32, "simvgb_head_xattn: at most 32 queries per sample (got %d)", nq);
+    const int kv_smem = 2 * nq * XH * XK * (int)sizeof(float);
+    SIMVGB_CHECK(ensure_dynamic_smem((const void*)xattn_bwd_kv_kernel, 2 * 32 * XH * XK * (int)sizeof(float)) == 0,
+                 "simvgb_head_xattn: shared memory opt-in failed");
+    xattn_absorb_kernel<<<R, 256, 0, st>>>(a->q, a->Wk, a->bk, u, c, a->scale);
+    xattn_absorb_kernel<<<R, 256, 0, st>>>(a->dctx, a->Wv, a->bv, dz, dps, 1.f);
+    xattn_dot_kernel<<<tiles, 256, dot_smem, st>>>(dz, dps, a->val, nullptr, dP, nq, N);
+    xattn_softmax_bwd_kernel<<<(int)((RH + 3) / 4), 128, 0, st>>>(dP, a->P, a->drop_u, dc, (int)RH, N, a->drop_p);
+    xattn_wsum_kernel<<<chunks, 256, 0, st>>>(dP, nullptr, a->kin, part, nq, N, pl.CL, 0.f);
+    xattn_bwd_kv_kernel<<<tiles, 256, kv_smem, st>>>(dP, a->P, a->drop_u, u, dz, a->dkin, a->dval, nq, N, a->drop_p);
+    xattn_out_kernel<<<R, 256, 0, st>>>(part, pl.NC, dc, a->Wk, a->bk, du, a->dq, a->scale, 1, R);
+    xattn_bwd_w_kernel<<<dim3(XE / 32, XH), 256, 0, st>>>(a->q, du, dc, a->dWk, a->dbk, a->scale, R);
+    xattn_bwd_w_kernel<<<dim3(XE / 32, XH), 256, 0, st>>>(a->dctx, a->z, a->psum, a->dWv, a->dbv, 1.f, R);
   }
   SIMVGB_CUDA(cudaGetLastError());
   return 0;

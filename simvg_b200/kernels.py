@@ -106,6 +106,8 @@ def _lib_setup():
                                             L.c_f32, L.c_f32, L.c_int, L.c_vp, L.c_f32, L.c_vp, L.c_f32, L.c_vp]
         lib.simvgb_adam_amsgrad_dev.argtypes = [L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_vp, L.c_i64, L.c_vp, L.c_f32, L.c_f32,
                                                 L.c_f32, L.c_f32, L.c_vp, L.c_f32, L.c_vp, L.c_vp]
+        lib.simvgb_head_xattn_ws_floats.argtypes = [L.c_int, L.c_int, L.c_int, L.c_int]
+        lib.simvgb_head_xattn_ws_floats.restype = ctypes.c_longlong
         lib._simvgb_typed = True
     return lib
 
@@ -458,7 +460,8 @@ class HeadXAttnArgs(ctypes.Structure):
                 ("kpm", L.c_vp), ("drop_u", L.c_vp), ("ctx", L.c_vp), ("P", L.c_vp), ("z", L.c_vp), ("psum", L.c_vp),
                 ("dctx", L.c_vp), ("dq", L.c_vp), ("dkin", L.c_vp), ("dval", L.c_vp), ("dWk", L.c_vp), ("dbk", L.c_vp),
                 ("dWv", L.c_vp), ("dbv", L.c_vp),
-                ("B", L.c_int), ("nq", L.c_int), ("N", L.c_int), ("E", L.c_int), ("H", L.c_int), ("drop_p", L.c_f32), ("scale", L.c_f32)]
+                ("B", L.c_int), ("nq", L.c_int), ("N", L.c_int), ("E", L.c_int), ("H", L.c_int), ("drop_p", L.c_f32), ("scale", L.c_f32),
+                ("ws", L.c_vp), ("ws_floats", ctypes.c_longlong)]
 
 
 def _f32c(t):
@@ -564,6 +567,14 @@ def _xattn_args(q, kin, val, Wk, bk, Wv, bv, B, nq, N, kpm, drop_u, drop_p):
     return a
 
 
+def _xattn_ws(lib, a, B, nq, N, backward, dev):
+    """Scratch of one absorbed cross-attention call (stream-ordered: freed back to the caching allocator right after the launch)."""
+    n = lib.simvgb_head_xattn_ws_floats(B, nq, N, backward)
+    ws = torch.empty(n, device=dev, dtype=f32)
+    a.ws, a.ws_floats = ws.data_ptr(), n
+    return ws
+
+
 def head_xattn_fwd(q, kin, val, Wk, bk, Wv, bv, B, nq, N, kpm=None, drop_u=None, drop_p=0.0):
     """Absorbed-projection cross-attention over the image memory -> (ctx [B*nq, 256], P [B*nq, 8, N], z [B*nq, 8, 256], psum [B*nq, 8])."""
     L.require_device(q)
@@ -575,8 +586,10 @@ def head_xattn_fwd(q, kin, val, Wk, bk, Wv, bv, B, nq, N, kpm=None, drop_u=None,
     psum = torch.empty(R, 8, device=q.device, dtype=f32)
     a = _xattn_args(q, kin, val, Wk, bk, Wv, bv, B, nq, N, kpm, drop_u, drop_p)
     a.ctx, a.P, a.z, a.psum = ctx.data_ptr(), P.data_ptr(), z.data_ptr(), psum.data_ptr()
+    ws = _xattn_ws(lib, a, B, nq, N, 0, q.device)
     L.check(lib.simvgb_head_xattn(ctypes.byref(a), 0, L.c_vp(_stream())), "head_xattn_fwd")
-    _launches[0] += 1
+    del ws
+    _launches[0] += 5
     return ctx, P, z, psum
 
 
@@ -586,5 +599,7 @@ def head_xattn_bwd(dctx, q, kin, val, Wk, bk, Wv, bv, P, z, psum, B, nq, N, dq, 
     a = _xattn_args(q, kin, val, Wk, bk, Wv, bv, B, nq, N, kpm, drop_u, drop_p)
     a.P, a.z, a.psum, a.dctx = P.data_ptr(), z.data_ptr(), psum.data_ptr(), _p(_f32c(dctx))
     a.dq, a.dkin, a.dval, a.dWk, a.dbk, a.dWv, a.dbv = (t.data_ptr() for t in (dq, dkin, dval, dWk, dbk, dWv, dbv))
+    ws = _xattn_ws(lib, a, B, nq, N, 1, q.device)
     L.check(lib.simvgb_head_xattn(ctypes.byref(a), 1, L.c_vp(_stream())), "head_xattn_bwd")
-    _launches[0] += 1
+    del ws
+    _launches[0] += 9

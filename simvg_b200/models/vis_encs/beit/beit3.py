@@ -150,6 +150,8 @@ class BEIT3(nn.Module):
         self.drop_path_probs = [float(p) for p in np.linspace(0, dpr, L)] if dpr > 0 else [0.0] * L
         self._flat = None
         self._attn_ws = {}
+        self._defer_backward = False   # simvg_b200.runtime.GraphedTrainStep (N > 1): backward is stashed in _deferred, run in chunks
+        self._deferred = None
         self._ddp = None   # set by simvg_b200.optim.FlatDDP: gradient ranges are all-reduced as they become final
         # Data-parallel runs exchange the text-embedding gradient as (ids, rows) instead of the dense [vocab, D] table:
         # FlatDDP sets "defer", the backward then leaves the compact form here (simvg_b200/optim.py::_exchange_text_rows).
@@ -383,106 +385,147 @@ def encoder_forward(mod, image, ids, pad_mask, save):
     return outs[0].view(B, Lv, D), outs[1].view(B, Lt, D), ctx
 
 
+def layer_flat_range(mod, li):
+    """Flat-buffer element range [lo, hi) holding every parameter of encoder layer li (both experts).  The buffer is laid out
+    [embeddings + final LayerNorms | layer 0 | layer 1 | ...], so range(0)[0] is also the end of the global parameters."""
+    nf = len(_GROUP_FIELDS)
+    fb = mod.flat()
+    i0 = mod._n_global + li * 2 * nf
+    i1 = i0 + 2 * nf
+    return fb.offsets[i0], (fb.offsets[i1] if i1 < len(fb.offsets) else fb.numel)
+
+
+class EncoderBackward:
+    """The encoder backward as a resumable sequence: start() (final LayerNorms), layers(hi, lo) (any contiguous block of layers,
+    top down), finish() (embeddings).  `encoder_backward` runs it in one go; the multi-GPU graph runtime
+    (simvg_b200/runtime.py) captures it in chunks so that the gradient exchange of one chunk overlaps the next chunk's kernels.
+    Writes (accumulates) every encoder parameter gradient into the flat gradient buffer."""
+
+    def __init__(self, mod, ctx, dxv, dxt):
+        self.mod, self.ctx = mod, ctx
+        cfg = mod.cfg
+        self.D, self.H, self.F, self.P = cfg["embed_dim"], cfg["heads"], cfg["ffn_dim"], cfg["patch_size"]
+        self.B, self.N, self.Lv, self.Lt = ctx["shape"]
+        self.Rs, self.Ls = (self.B * self.Lv, self.B * self.Lt), (self.Lv, self.Lt)
+        self.fb = mod.flat()
+        self.glob, self.layer_views = ctx["views"]
+        self.dev = dxv.device
+        self.ddp = getattr(mod, "_ddp", None)
+        self.nl = len(self.layer_views)
+        self.dys = (dxv.reshape(self.Rs[0], self.D).contiguous().float(), dxt.reshape(self.Rs[1], self.D).contiguous().float())
+        self.dres = [None, None]
+        self.dyb = None
+
+    def layer_range(self, li):
+        return layer_flat_range(self.mod, li)
+
+    def start(self):
+        ctx, glob, layers, nl, Rs, Ls, D, dev = self.ctx, self.glob, self.layer_views, self.nl, self.Rs, self.Ls, self.D, self.dev
+        if self.ddp is not None:
+            self.ddp.on_encoder_backward_start()
+        self.dyb = [torch.empty(Rs[g], D, device=dev, dtype=bf16) for g in range(2)]
+        for g, which in enumerate(("A", "B")):
+            xf, mF, rF = ctx["fin"][g]
+            Gl = layers[nl - 1][g]
+            self.dres[g] = torch.empty(Rs[g], D, device=dev, dtype=f32)
+            K.ln_bwd(0, xf, self.dys[g], glob["fin_%s_w" % which][0], mF, rF, glob["fin_%s_w" % which][2], glob["fin_%s_b" % which][2],
+                     dres_in=None, dres_out=self.dres[g], dyb=self.dyb[g], row_scale=ctx["layers"][nl - 1]["dp"][1],
+                     rows_per_scale=Ls[g], dbias_prev=Gl.g["fc2_b"])
+
+    def layers(self, hi, lo):
+        mod, ctx, layers, Rs, Ls, dev = self.mod, self.ctx, self.layer_views, self.Rs, self.Ls, self.dev
+        D, H, F, B, Lv, Lt = self.D, self.H, self.F, self.B, self.Lv, self.Lt
+        dres, dyb, fb, ddp = self.dres, self.dyb, self.fb, self.ddp
+        nf = len(_GROUP_FIELDS)
+        for li in range(hi, lo - 1, -1):
+            sl = ctx["layers"][li]
+            dp1, _dp2 = sl["dp"]
+            Gs = layers[li]
+            svs = sl["g"]
+            # ---- FFN:  x = xmid + dp2 * fc2(LN_F(gelu(fc1(LN2(xmid)))))      (each GEMM: both experts in one launch)
+            K.wgrad_pair(*[(dyb[g], svs[g]["f"], D, F, Rs[g], Gs[g].g["fc2_w"]) for g in range(2)])
+            df = K.gemm_pair(*[(dyb[g], Gs[g].wb["fc2_w"], Rs[g], F, D, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
+            du = [torch.empty(Rs[g], F, device=dev, dtype=bf16) for g in range(2)]
+            for g, G in enumerate(Gs):
+                K.ln_bwd(2, None, df[g], G.w["fl_w"], svs[g]["mf"], svs[g]["rf"], G.g["fl_w"], G.g["fl_b"], dx=du[g], u=svs[g]["u"],
+                         dbias_prev=G.g["fc1_b"])
+            del df
+            K.wgrad_pair(*[(du[g], svs[g]["h2"], F, D, Rs[g], Gs[g].g["fc1_w"]) for g in range(2)])
+            dh2 = K.gemm_pair(*[(du[g], Gs[g].wb["fc1_w"], Rs[g], D, F, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
+            del du
+            for g, G in enumerate(Gs):
+                K.ln_bwd(0, svs[g]["xmid"], dh2[g], G.w["ln2_w"], svs[g]["m2"], svs[g]["r2"], G.g["ln2_w"], G.g["ln2_b"], dres_in=dres[g],
+                         dres_out=dres[g], dyb=dyb[g], row_scale=dp1, rows_per_scale=Ls[g], dbias_prev=G.g["o_b"])
+            del dh2
+            # ---- attention output:  xmid = x_in + dp1 * out_proj(LN_inner(O))
+            K.wgrad_pair(*[(dyb[g], svs[g]["a"], D, D, Rs[g], Gs[g].g["o_w"]) for g in range(2)])
+            da = K.gemm_pair(*[(dyb[g], Gs[g].wb["o_w"], Rs[g], D, D, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
+            dO = [torch.empty(Rs[g], D, device=dev, dtype=bf16) for g in range(2)]
+            ws = K.attn_workspace(mod._attn_ws, B, H, Lv, Lt, dev)
+            for g, G in enumerate(Gs):
+                # the inner-attention-LN backward also emits delta = rowsum(O o dO) per head for the attention backward
+                K.ln_bwd(1, svs[g]["o"], da[g], G.w["in_w"], svs[g]["mi"], svs[g]["ri"], G.g["in_w"], G.g["in_b"], dx=dO[g],
+                         delta=K.attn_delta_spec(ws, B, H, Lv, Lt, g))
+            del da
+            svv, svt = svs
+            dqkv = K.attn_bwd(svv["qkv"], svt["qkv"], ctx["pad"], svv["o"], svt["o"], sl["lse"], dO[0], dO[1], B, H, Lv, Lt,
+                              ws=ws, delta_ready=True)
+            for g, G in enumerate(Gs):
+                K.colsum(dqkv[g], out=G.gbqkv)
+            K.wgrad_pair(*[(dqkv[g], svs[g]["h"], 3 * D, D, Rs[g], Gs[g].gWqkv) for g in range(2)])
+            dh = K.gemm_pair(*[(dqkv[g], Gs[g].Wqkv, Rs[g], D, 3 * D, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
+            for g, G in enumerate(Gs):
+                sv = svs[g]
+                if li > 0:
+                    Gp = layers[li - 1][g]
+                    K.ln_bwd(0, sv["x_in"], dh[g], G.w["ln1_w"], sv["m1"], sv["r1"], G.g["ln1_w"], G.g["ln1_b"], dres_in=dres[g],
+                             dres_out=dres[g], dyb=dyb[g], row_scale=ctx["layers"][li - 1]["dp"][1], rows_per_scale=Ls[g],
+                             dbias_prev=Gp.g["fc2_b"])
+                else:
+                    K.ln_bwd(0, sv["x_in"], dh[g], G.w["ln1_w"], sv["m1"], sv["r1"], G.g["ln1_w"], G.g["ln1_b"], dres_in=dres[g],
+                             dres_out=dres[g])
+            del dh
+            ctx["layers"][li] = None  # release this layer's activations
+            if li > 0:
+                # every gradient of layer li is final now (its fc2 bias was written by layer li+1's LN1 backward)
+                i0 = mod._n_global + li * 2 * nf
+                i1 = i0 + 2 * nf
+                _zero_frozen(fb, i0, i1)   # BEFORE the range is handed to the (asynchronous, in-place) all-reduce
+            if ddp is not None and li > 0:
+                ddp.on_encoder_range_done(fb.offsets[i0], fb.offsets[i1] if i1 < len(fb.offsets) else fb.numel)
+
+    def finish(self):
+        mod, ctx, glob, dres, fb, ddp, dev = self.mod, self.ctx, self.glob, self.dres, self.fb, self.ddp, self.dev
+        B, N, Lv, Lt, D, P = self.B, self.N, self.Lv, self.Lt, self.D, self.P
+        nf = len(_GROUP_FIELDS)
+        # ---- embeddings (Encoder.forward_embedding, beit3_base.py:317-334 ; VisionEmbedding / TextEmbedding A.6-A.7)
+        dv = dres[0].view(B, Lv, D)
+        glob["posA"][2][2:2 + Lv].add_(dv.sum(0))
+        glob["cls_token"][2].view(D).add_(dv[:, 0].sum(0))
+        dpatch = torch.empty(B * N, D, device=dev, dtype=bf16)
+        K.colsum(dv[:, 1:].reshape(B * N, D), out=glob["proj_b"][2], out_bf16=dpatch)
+        K.wgrad(dpatch, ctx["cols"], D, 3 * P * P, B * N, out=glob["proj_w"][2].view(D, 3 * P * P))
+        dt = dres[1].view(B, Lt, D)
+        if ctx["pad"] is not None:
+            dt = dt * (1.0 - ctx["pad"].view(B, Lt, 1).float())
+        glob["posB"][2][2:2 + Lt].add_(dt.sum(0))
+        st = mod.sparse_text_grad
+        if st["defer"]:   # data parallel: ranks all-gather these <= B*Lt rows instead of all-reducing the dense table
+            st["ids"], st["rows"] = ctx["ids"].reshape(-1), dt.reshape(B * Lt, D).contiguous()
+        else:
+            glob["text_embed"][2].index_add_(0, ctx["ids"].reshape(-1), dt.reshape(B * Lt, D))
+        _zero_frozen(fb, 0, mod._n_global + 2 * nf)
+        if ddp is not None:   # layer 0 + the embedding / final-LN parameters at the front of the buffer
+            i1 = mod._n_global + 2 * nf
+            ddp.on_encoder_range_done(0, fb.offsets[i1] if i1 < len(fb.offsets) else fb.numel)
+
+
 def encoder_backward(mod, ctx, dxv, dxt):
     """Writes (accumulates) every encoder parameter gradient into the flat gradient buffer."""
-    cfg = mod.cfg
-    D, H, F, P = cfg["embed_dim"], cfg["heads"], cfg["ffn_dim"], cfg["patch_size"]
-    B, N, Lv, Lt = ctx["shape"]
-    Rs, Ls = (B * Lv, B * Lt), (Lv, Lt)
-    fb = mod.flat()
-    glob, layers = ctx["views"]
-    dev = dxv.device
-    ddp = getattr(mod, "_ddp", None)
-    nf = len(_GROUP_FIELDS)
-    if ddp is not None:
-        ddp.on_encoder_backward_start()
-    dres = [None, None]
-    dyb = [torch.empty(Rs[g], D, device=dev, dtype=bf16) for g in range(2)]
-    nl = len(layers)
-    dys = (dxv.reshape(Rs[0], D).contiguous().float(), dxt.reshape(Rs[1], D).contiguous().float())
-    for g, which in enumerate(("A", "B")):
-        xf, mF, rF = ctx["fin"][g]
-        Gl = layers[nl - 1][g]
-        dres[g] = torch.empty(Rs[g], D, device=dev, dtype=f32)
-        K.ln_bwd(0, xf, dys[g], glob["fin_%s_w" % which][0], mF, rF, glob["fin_%s_w" % which][2], glob["fin_%s_b" % which][2],
-                 dres_in=None, dres_out=dres[g], dyb=dyb[g], row_scale=ctx["layers"][nl - 1]["dp"][1], rows_per_scale=Ls[g],
-                 dbias_prev=Gl.g["fc2_b"])
-    for li in range(nl - 1, -1, -1):
-        sl = ctx["layers"][li]
-        dp1, _dp2 = sl["dp"]
-        Gs = layers[li]
-        svs = sl["g"]
-        # ---- FFN:  x = xmid + dp2 * fc2(LN_F(gelu(fc1(LN2(xmid)))))      (each GEMM: both experts in one launch)
-        K.wgrad_pair(*[(dyb[g], svs[g]["f"], D, F, Rs[g], Gs[g].g["fc2_w"]) for g in range(2)])
-        df = K.gemm_pair(*[(dyb[g], Gs[g].wb["fc2_w"], Rs[g], F, D, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
-        du = [torch.empty(Rs[g], F, device=dev, dtype=bf16) for g in range(2)]
-        for g, G in enumerate(Gs):
-            K.ln_bwd(2, None, df[g], G.w["fl_w"], svs[g]["mf"], svs[g]["rf"], G.g["fl_w"], G.g["fl_b"], dx=du[g], u=svs[g]["u"],
-                     dbias_prev=G.g["fc1_b"])
-        del df
-        K.wgrad_pair(*[(du[g], svs[g]["h2"], F, D, Rs[g], Gs[g].g["fc1_w"]) for g in range(2)])
-        dh2 = K.gemm_pair(*[(du[g], Gs[g].wb["fc1_w"], Rs[g], D, F, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
-        del du
-        for g, G in enumerate(Gs):
-            K.ln_bwd(0, svs[g]["xmid"], dh2[g], G.w["ln2_w"], svs[g]["m2"], svs[g]["r2"], G.g["ln2_w"], G.g["ln2_b"], dres_in=dres[g],
-                     dres_out=dres[g], dyb=dyb[g], row_scale=dp1, rows_per_scale=Ls[g], dbias_prev=G.g["o_b"])
-        del dh2
-        # ---- attention output:  xmid = x_in + dp1 * out_proj(LN_inner(O))
-        K.wgrad_pair(*[(dyb[g], svs[g]["a"], D, D, Rs[g], Gs[g].g["o_w"]) for g in range(2)])
-        da = K.gemm_pair(*[(dyb[g], Gs[g].wb["o_w"], Rs[g], D, D, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
-        dO = [torch.empty(Rs[g], D, device=dev, dtype=bf16) for g in range(2)]
-        ws = K.attn_workspace(mod._attn_ws, B, H, Lv, Lt, dev)
-        for g, G in enumerate(Gs):
-            # the inner-attention-LN backward also emits delta = rowsum(O o dO) per head for the attention backward
-            K.ln_bwd(1, svs[g]["o"], da[g], G.w["in_w"], svs[g]["mi"], svs[g]["ri"], G.g["in_w"], G.g["in_b"], dx=dO[g],
-                     delta=K.attn_delta_spec(ws, B, H, Lv, Lt, g))
-        del da
-        svv, svt = svs
-        dqkv = K.attn_bwd(svv["qkv"], svt["qkv"], ctx["pad"], svv["o"], svt["o"], sl["lse"], dO[0], dO[1], B, H, Lv, Lt,
-                          ws=ws, delta_ready=True)
-        for g, G in enumerate(Gs):
-            K.colsum(dqkv[g], out=G.gbqkv)
-        K.wgrad_pair(*[(dqkv[g], svs[g]["h"], 3 * D, D, Rs[g], Gs[g].gWqkv) for g in range(2)])
-        dh = K.gemm_pair(*[(dqkv[g], Gs[g].Wqkv, Rs[g], D, 3 * D, dict(b_mn=True, epilogue=K.EPI_BF16)) for g in range(2)])
-        for g, G in enumerate(Gs):
-            sv = svs[g]
-            if li > 0:
-                Gp = layers[li - 1][g]
-                K.ln_bwd(0, sv["x_in"], dh[g], G.w["ln1_w"], sv["m1"], sv["r1"], G.g["ln1_w"], G.g["ln1_b"], dres_in=dres[g],
-                         dres_out=dres[g], dyb=dyb[g], row_scale=ctx["layers"][li - 1]["dp"][1], rows_per_scale=Ls[g],
-                         dbias_prev=Gp.g["fc2_b"])
-            else:
-                K.ln_bwd(0, sv["x_in"], dh[g], G.w["ln1_w"], sv["m1"], sv["r1"], G.g["ln1_w"], G.g["ln1_b"], dres_in=dres[g],
-                         dres_out=dres[g])
-        del dh
-        ctx["layers"][li] = None  # release this layer's activations
-        if li > 0:
-            # every gradient of layer li is final now (its fc2 bias was written by layer li+1's LN1 backward)
-            i0 = mod._n_global + li * 2 * nf
-            i1 = i0 + 2 * nf
-            _zero_frozen(fb, i0, i1)   # BEFORE the range is handed to the (asynchronous, in-place) all-reduce
-        if ddp is not None and li > 0:
-            ddp.on_encoder_range_done(fb.offsets[i0], fb.offsets[i1] if i1 < len(fb.offsets) else fb.numel)
-    # ---- embeddings (Encoder.forward_embedding, beit3_base.py:317-334 ; VisionEmbedding / TextEmbedding A.6-A.7)
-    dv = dres[0].view(B, Lv, D)
-    glob["posA"][2][2:2 + Lv].add_(dv.sum(0))
-    glob["cls_token"][2].view(D).add_(dv[:, 0].sum(0))
-    dpatch = torch.empty(B * N, D, device=dev, dtype=bf16)
-    K.colsum(dv[:, 1:].reshape(B * N, D), out=glob["proj_b"][2], out_bf16=dpatch)
-    K.wgrad(dpatch, ctx["cols"], D, 3 * P * P, B * N, out=glob["proj_w"][2].view(D, 3 * P * P))
-    dt = dres[1].view(B, Lt, D)
-    if ctx["pad"] is not None:
-        dt = dt * (1.0 - ctx["pad"].view(B, Lt, 1).float())
-    glob["posB"][2][2:2 + Lt].add_(dt.sum(0))
-    st = mod.sparse_text_grad
-    if st["defer"]:   # data parallel: ranks all-gather these <= B*Lt rows instead of all-reducing the dense table
-        st["ids"], st["rows"] = ctx["ids"].reshape(-1), dt.reshape(B * Lt, D).contiguous()
-    else:
-        glob["text_embed"][2].index_add_(0, ctx["ids"].reshape(-1), dt.reshape(B * Lt, D))
-    _zero_frozen(fb, 0, mod._n_global + 2 * nf)
-    if ddp is not None:   # layer 0 + the embedding / final-LN parameters at the front of the buffer
-        i1 = mod._n_global + 2 * nf
-        ddp.on_encoder_range_done(0, fb.offsets[i1] if i1 < len(fb.offsets) else fb.numel)
+    eb = EncoderBackward(mod, ctx, dxv, dxt)
+    eb.start()
+    eb.layers(eb.nl - 1, 0)
+    eb.finish()
 
 
 def _zero_frozen(fb, i0, i1):
@@ -516,6 +559,10 @@ class _EncoderFn(torch.autograd.Function):
         if dxt is None:
             dxt = torch.zeros(B, Lt, D, device=dev)
         with torch.no_grad():
-            encoder_backward(mod, saved, dxv, dxt)
+            if getattr(mod, "_defer_backward", False):
+                # the multi-GPU graph runtime runs the encoder backward itself, in separately captured chunks
+                mod._deferred = EncoderBackward(mod, saved, dxv, dxt)
+            else:
+                encoder_backward(mod, saved, dxv, dxt)
         ctx.saved = None
         return None, None, None, None, torch.zeros(1, device=dev)

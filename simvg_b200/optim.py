@@ -373,6 +373,29 @@ class FlatDDP:
         if self._skip is not None:
             self._exchange_text_rows()
 
+    # ---- chunked graph runtime (simvg_b200/runtime.py): collectives are issued BETWEEN the replays of the backward chunks
+    def reduce_async(self, lo=None, hi=None, heads=False):
+        """Asynchronous all-reduce of encoder-segment elements [lo, hi) and / or (heads=True) of every other segment.  NCCL
+        orders it after the work already enqueued on the current stream; later launches on that stream overlap it."""
+        if self.world <= 1:
+            return
+        if heads:
+            for s in self.opt.segments:
+                if s is not self._enc_seg:
+                    self._reduce(s.fb.grad)
+        if lo is not None:
+            self._reduce_range(lo, hi)
+
+    def wait(self):
+        """The current stream waits for every outstanding all-reduce; then the sparse text-embedding rows are exchanged."""
+        for w, buf in self._work:
+            w.wait()
+            if buf is not None:
+                buf.div_(self.world)
+        self._work = []
+        if self.world > 1 and self._skip is not None:
+            self._exchange_text_rows()
+
     def finish(self):
         """Call after backward(): waits for the outstanding all-reduces (and reduces anything not yet sent)."""
         if self.world <= 1:
@@ -385,10 +408,4 @@ class FlatDDP:
                     self._reduce_range(0, s.fb.numel)
                 else:
                     self._reduce(s.fb.grad)
-        for w, buf in self._work:
-            w.wait()
-            if buf is not None:
-                buf.div_(self.world)
-        self._work = []
-        if self._skip is not None:
-            self._exchange_text_rows()
+        self.wait()

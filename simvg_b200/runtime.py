@@ -8,10 +8,13 @@ step-invariant: inputs are copied into static buffers, the optimiser reads its s
 synchronisation on the REC path.
 
   1 GPU : ONE graph  = zero_grad + forward + losses + backward + clip + Adam(+EMA).
-  N GPUs: TWO graphs = [zero_grad + forward + losses + backward]  ->  gradient exchange (NCCL, launched between the
-          graphs on the same stream: all-reduce of the flat gradient ranges + all-gather of the text-embedding rows)  ->
-          [clip + Adam(+EMA)].  No collective is captured (capturing them hung in round 1), every rank replays exactly the
-          launch sequence the 1-GPU number is quoted on, and the only exposed communication is one ~0.7 GB all-reduce.
+  N GPUs: the backward is cut into CHUNKS of encoder layers, each its own graph:
+          [zero_grad + forward + losses + head backward] -> [encoder layers 11..10] -> [9..8] -> ... -> [1] ->
+          [0 + embeddings] -> [clip + Adam(+EMA)].  After each chunk's replay the flat gradient range that chunk finished is handed to an
+          asynchronous NCCL all-reduce (FlatDDP.reduce_async), which runs under the following chunks' kernels; only the last
+          chunk's range (layer 0 + embeddings, ~60 MB for ViT-B) and the all-gather of the text-embedding rows are exposed.
+          No collective is captured (capturing them hung in round 1) and every rank replays exactly the launch sequence the
+          1-GPU number is quoted on.  `chunk_layers=0` keeps the backward in one graph and exchanges everything after it.
 """
 import torch
 
@@ -29,20 +32,30 @@ class GraphedTrainStep:
     shape and share one memory pool, so alternating between shapes does not re-capture.  Returned tensors are the graph's
     static outputs (overwritten by the next call with the same shape)."""
 
-    def __init__(self, model, optimizer, ddp=None, warmup=1):
+    def __init__(self, model, optimizer, ddp=None, warmup=1, chunk_layers=None):
         self.model, self.opt, self.warmup = model, optimizer, max(1, int(warmup))
         self.ddp = ddp if (ddp is not None and ddp.world > 1) else None
         if self.ddp is not None and not self.ddp.deferred:
-            raise ValueError("GraphedTrainStep needs FlatDDP(..., deferred=True): collectives run between the two step graphs")
-        self.graph = None        # fwd + bwd (+ optimiser when single-GPU)
-        self.graph_opt = None    # optimiser graph (multi-GPU)
+            raise ValueError("GraphedTrainStep needs FlatDDP(..., deferred=True): collectives run between the step's graphs")
+        enc = getattr(model, "vis_enc", None)
+        can_chunk = enc is not None and hasattr(enc, "_defer_backward")
+        if chunk_layers is None:
+            chunk_layers = 2 if (self.ddp is not None and can_chunk) else 0
+        self.chunk_layers = int(chunk_layers) if can_chunk else 0
+        self.plan = None         # [(graph, exchange)]: exchange = None | "all" | (lo, hi, heads) handed to the process group after the replay
+        self.graph_opt = None    # optimiser graph (when the step is more than one graph)
         self.key = None
         self.static = None
         self.out = None
         self.launches_per_step = 0
-        self._cache = {}         # key -> (graph, graph_opt, static, out, launches, text-gradient mailbox)
+        self._cache = {}         # key -> (plan, graph_opt, static, out, launches, text-gradient mailbox, deferred backward)
         self._pool = None
         self._mail = None        # (ids, rows) tensors this graph's backward writes for the sparse text-embedding exchange
+        self._eb = None          # the captured EncoderBackward (its buffers live across the chunk graphs)
+
+    @property
+    def graph(self):
+        return None if self.plan is None else self.plan[0][0]
 
     def _fwd_bwd(self, d, metas):
         self.opt.zero_grad()
@@ -50,6 +63,12 @@ class GraphedTrainStep:
                                    gt_bbox=list(d["gt"].unbind(0)), rescale=False)
         losses["loss_total"].backward()
         return losses, preds
+
+    def _chunks(self, nl):
+        """[(hi, lo)] top-down; layer 0 (+ embeddings) always last and alone: its exchange is the exposed one."""
+        cl = self.chunk_layers
+        out = [(hi, max(hi - cl + 1, 1)) for hi in range(nl - 1, 0, -cl)]
+        return out + [(0, 0)]
 
     def _capture(self, img, ids, metas, mask, gt):
         dev = next(self.model.parameters()).device
@@ -72,23 +91,64 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         K.reset_launch_count()
-        self.graph = torch.cuda.CUDAGraph()
         # a process group's watchdog thread may touch CUDA while we capture: police this thread's calls only
         mode = "thread_local" if self.ddp is not None else "global"
-        # graphs of different input shapes share one memory pool when they are the only thing running between replays; with a
-        # process group the eager exchange sits between the two graphs of a step, so every shape keeps its own pool there
-        kw = {} if (self._pool is None or self.ddp is not None) else {"pool": self._pool}
-        with torch.cuda.graph(self.graph, stream=side, capture_error_mode=mode, **kw):   # same stream as the warm-up: autograd's AccumulateGrad nodes stay on it
-            losses, preds = self._fwd_bwd(self.static, metas)
-            if self.ddp is None:
+        multi = self.ddp is not None or self.chunk_layers > 0
+        # single-graph steps of different input shapes share one memory pool (nothing else runs between replays); a
+        # multi-graph step has eager collectives between its graphs, so every shape keeps its own pool (shared by its graphs)
+        pool = None if multi else self._pool
+        enc = getattr(self.model, "vis_enc", None)
+        self.plan, self._eb = [], None
+
+        def capture(body):
+            nonlocal pool
+            g = torch.cuda.CUDAGraph()
+            kw = {} if pool is None else {"pool": pool}
+            # same stream as the warm-up: autograd's AccumulateGrad nodes stay on it
+            with torch.cuda.graph(g, stream=side, capture_error_mode=mode, **kw):
+                res = body()
+            if pool is None:
+                pool = g.pool()
+            return g, res
+
+        def first():
+            if self.chunk_layers > 0:
+                enc._defer_backward = True
+            try:
+                res = self._fwd_bwd(self.static, metas)
+            finally:
+                if self.chunk_layers > 0:
+                    enc._defer_backward = False
+            if self.chunk_layers > 0:
+                self._eb, enc._deferred = enc._deferred, None
+                if self._eb is None:
+                    raise RuntimeError("the encoder backward did not run inside loss.backward(): nothing to chunk")
+                self._eb.start()
+            elif not multi:
                 self.opt.step()
-        if self._pool is None or self.ddp is not None:
-            self._pool = self.graph.pool()
+            return res
+
+        if self.chunk_layers > 0:
+            g, (losses, preds) = capture(first)
+            self.plan.append((g, (None, None, True)))       # head gradients are final once autograd reached the encoder node
+            eb = self._eb
+            for hi, lo in self._chunks(eb.nl):
+                def body(hi=hi, lo=lo):
+                    with torch.no_grad():
+                        eb.layers(hi, lo)
+                        if lo == 0:
+                            eb.finish()
+                g, _ = capture(body)
+                rng = (eb.layer_range(lo)[0], eb.layer_range(hi)[1]) if lo > 0 else (0, eb.layer_range(0)[1])
+                self.plan.append((g, (rng[0], rng[1], False)))
+        else:
+            g, (losses, preds) = capture(first)
+            self.plan.append((g, "all" if self.ddp is not None else None))
+        if not multi:
+            self._pool = pool
         self.graph_opt = None
-        if self.ddp is not None:
-            self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt, stream=side, capture_error_mode=mode, pool=self._pool):
-                self.opt.step()
+        if multi:
+            self.graph_opt, _ = capture(self.opt.step)
         self.launches_per_step = K.launch_count()
         self.out = (losses, preds)
         st = getattr(getattr(self.model, "vis_enc", None), "sparse_text_grad", None)
@@ -106,10 +166,10 @@ class GraphedTrainStep:
         key = (tuple(img.shape), img.dtype, tuple(ref_expr_inds.shape), tuple(tuple(m["img_shape"][:2]) for m in img_metas))
         if key != self.key:
             if self.key is not None:
-                self._cache[self.key] = (self.graph, self.graph_opt, self.static, self.out, self.launches_per_step, self._mail)
+                self._cache[self.key] = (self.plan, self.graph_opt, self.static, self.out, self.launches_per_step, self._mail, self._eb)
             self.key = key
             if key in self._cache:
-                self.graph, self.graph_opt, self.static, self.out, self.launches_per_step, self._mail = self._cache[key]
+                self.plan, self.graph_opt, self.static, self.out, self.launches_per_step, self._mail, self._eb = self._cache[key]
                 st = getattr(getattr(self.model, "vis_enc", None), "sparse_text_grad", None)
                 if st is not None and self._mail is not None:
                     st["ids"], st["rows"] = self._mail      # the exchange reads the buffers THIS graph's backward fills
@@ -120,8 +180,15 @@ class GraphedTrainStep:
         else:
             self._upload(img, ref_expr_inds, text_attention_mask, gt_boxes)
         self.opt.advance()
-        self.graph.replay()
-        if self.ddp is not None:
-            self.ddp.exchange()
+        for g, ex in self.plan:
+            g.replay()
+            if self.ddp is not None and ex is not None:
+                if ex == "all":
+                    self.ddp.exchange()
+                else:
+                    self.ddp.reduce_async(ex[0], ex[1], heads=ex[2])
+        if self.ddp is not None and self.chunk_layers > 0:
+            self.ddp.wait()
+        if self.graph_opt is not None:
             self.graph_opt.replay()
         return self.out

@@ -98,7 +98,7 @@ def _worker_sparse(rank, world, port, out, deferred):
     torch.manual_seed(0)
     model = _ToyDet()
     opt = _Opt2(model)
-    ddp = FlatDDP(model, opt, deferred=deferred)
+    ddp = FlatDDP(model, opt, deferred=bool(deferred))
     assert model.vis_enc.sparse_text_grad["defer"]
     g = torch.Generator().manual_seed(100 + rank)
     ids = torch.randint(0, 50, (6,), generator=g)
@@ -116,16 +116,24 @@ def _worker_sparse(rank, world, port, out, deferred):
     if not deferred:
         ddp.on_encoder_backward_start()
         ddp.on_encoder_range_done(0, fb.numel)
-    ddp.finish()
+    if deferred == 2:     # the chunked graph runtime's sequence: heads, then encoder ranges top-down, then wait()
+        cut = fb.offsets[1] + 123                     # a boundary inside the sparsely exchanged table
+        ddp.reduce_async(heads=True)
+        ddp.reduce_async(cut, fb.numel)
+        ddp.reduce_async(0, cut)
+        ddp.wait()
+    else:
+        ddp.finish()
     torch.save({"local": local, "avg": [s_.fb.grad.clone() for s_ in opt.segments]}, os.path.join(out, "s%d_%d.pt" % (int(deferred), rank)))
     dist.destroy_process_group()
 
 
 def test_sparse_text_embedding_exchange_world2_gloo(tmp_path):
     """The text-embedding gradient travels as (ids, rows) per rank (all-gather + local scatter-add) while every other range is
-    all-reduced; both FlatDDP modes (overlap hooks / deferred exchange between the step graphs) must leave each rank with
+    all-reduced; all FlatDDP modes (overlap hooks / deferred exchange after the backward graph / asynchronous ranges between the chunked
+    backward graphs) must leave each rank with
     exactly the mean of the dense per-rank gradients."""
-    for deferred in (False, True):
+    for deferred in (0, 1, 2):
         port = _free_port()
         mp.spawn(_worker_sparse, args=(2, port, str(tmp_path), deferred), nprocs=2, join=True)
         r0 = torch.load(tmp_path / ("s%d_0.pt" % int(deferred)))

@@ -183,3 +183,43 @@ def test_graphed_train_step_matches_eager(lib):
     p2 = torch.cat([l2[i].detach().flatten() for i in keep])
     assert rel(p2, p1) < 2e-3, rel(p2, p1)
     assert preds[0]["pred_bboxes"].shape == (4, 4)
+
+
+@pytest.mark.gpu
+def test_chunked_backward_graphs_match_the_single_graph_step():
+    """The multi-GPU runtime's step (backward cut into per-layer-chunk graphs + a separate optimiser graph) run on ONE GPU, where
+    no collective sits between the chunks: same losses and parameters as the single-graph step."""
+    from simvg_b200.models import build_model
+    from simvg_b200.optim import FusedAdamAMSGrad
+    from simvg_b200.runtime import GraphedTrainStep
+    from tools.synth import make_batch, model_cfg
+
+    def run(chunk_layers):
+        torch.manual_seed(5)
+        m = build_model(model_cfg("base", 128, 32, drop_path_rate=0.0)).cuda().train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+            if isinstance(mod, torch.nn.MultiheadAttention):
+                mod.dropout = 0.0
+            if hasattr(mod, "attn_drop") and isinstance(mod.attn_drop, float):
+                mod.attn_drop = 0.0
+        o = FusedAdamAMSGrad(m, lr=2e-4, lr_vis_enc=2e-5, grad_norm_clip=0.15)
+        step = GraphedTrainStep(m, o, warmup=1, chunk_layers=chunk_layers)
+        batches = [make_batch(4, 128, seed=10 + i, device="cuda") for i in range(2)]
+        ls = []
+        for it in range(3):
+            b = batches[it % 2]
+            losses, _ = step(b["img"], b["ref_expr_inds"], b["img_metas"], b["text_attention_mask"], torch.stack(b["gt_bbox"]))
+            ls.append(float(losses["loss_total"]))
+        names = [n for n, _ in m.named_parameters()]
+        keep = [p.detach().flatten() for n, p in m.named_parameters() if "k_proj" not in n and "in_proj_bias" not in n]
+        return ls, torch.cat(keep), len(step.plan), step.graph_opt is not None, names
+
+    l0, p0, n0, opt0, _ = run(0)
+    l2, p2, n2, opt2, _ = run(2)
+    assert n0 == 1 and not opt0
+    assert n2 == 1 + 6 + 1 and opt2          # forward/head graph + chunks (11,10) .. (1,1) + (0,0); the optimiser graph is separate
+    for a, b in zip(l0, l2):
+        assert abs(a - b) <= 5e-3 * abs(a), (l0, l2)
+    assert float((p0 - p2).norm() / p0.norm()) < 2e-3

@@ -356,6 +356,51 @@ def test_head_lnres_and_small_attention_match_torch(lib):
             assert _mr(dq, q.grad) < 1e-4 and _mr(dk, k.grad) < 1e-4 and _mr(dv, v.grad) < 1e-4, (nq, nk)
 
 
+@pytest.mark.parametrize("B,nq,N,p", [(3, 1, 1600, 0.0), (2, 10, 100, 0.1), (2, 3, 333, 0.1), (1, 5, 40, 0.0)])
+def test_head_absorbed_cross_attention_matches_torch(lib, B, nq, N, p):
+    """simvgb_head_xattn (key-parallel passes, no atomics) against nn.MultiheadAttention arithmetic written out in torch with the
+    same dropout mask: context, saved probabilities, and every gradient (query, keys, values, both projections) — gradients
+    ACCUMULATE into their buffers, as the decoder stack relies on."""
+    from simvg_b200 import kernels as K
+    E, H = 256, 8
+    g = torch.Generator(device="cuda").manual_seed(11)
+    mk = lambda *s: torch.randn(*s, device=DEV, generator=g)  # noqa: E731
+    R = B * nq
+    q, kin, val = mk(R, E), mk(B * N, E), mk(B * N, E)
+    Wk, Wv, bk, bv = mk(E, E) * 0.06, mk(E, E) * 0.06, mk(E) * 0.1, mk(E) * 0.1
+    kpm = torch.zeros(B, N, dtype=torch.bool, device=DEV)
+    kpm[0, N // 3:] = True
+    u = torch.rand(R * H * N, device=DEV, generator=g) if p > 0 else None
+    dctx = mk(R, E)
+    scale = 32 ** -0.5
+    leaves = [t.clone().requires_grad_(True) for t in (q, kin, val, Wk, bk, Wv, bv)]
+    q_, kin_, val_, Wk_, bk_, Wv_, bv_ = leaves
+    kp = (kin_ @ Wk_.t() + bk_).view(B, N, H, 32).permute(0, 2, 1, 3)
+    vp = (val_ @ Wv_.t() + bv_).view(B, N, H, 32).permute(0, 2, 1, 3)
+    qh = (q_ * scale).view(B, nq, H, 32).permute(0, 2, 1, 3)
+    sc = (qh @ kp.transpose(-1, -2)).masked_fill(kpm[:, None, None, :], float("-inf"))
+    P_ref = sc.softmax(-1)                                       # [B, H, nq, N]
+    Pd = P_ref
+    if u is not None:
+        m = (u.view(B, nq, H, N).permute(0, 2, 1, 3) >= p).float() / (1 - p)
+        Pd = P_ref * m
+    ctx_ref = (Pd @ vp).permute(0, 2, 1, 3).reshape(R, E)
+    (ctx_ref * dctx).sum().backward()
+    ctx, P, z, psum = K.head_xattn_fwd(q, kin, val, Wk, bk, Wv, bv, B, nq, N, kpm=kpm.to(torch.uint8), drop_u=u, drop_p=p)
+    assert _mr(ctx, ctx_ref.detach()) < 2e-5
+    assert _mr(P.view(B, nq, H, N).permute(0, 2, 1, 3), P_ref.detach()) < 2e-5
+    base = 0.5
+    outs = [torch.full_like(t, base) for t in (q, kin, val, Wk, bk, Wv, bv)]
+    dq, dkin, dval, dWk, dbk, dWv, dbv = outs
+    K.head_xattn_bwd(dctx, q, kin, val, Wk, bk, Wv, bv, P, z, psum, B, nq, N, dq, dkin, dval, dWk, dbk, dWv, dbv,
+                     kpm=kpm.to(torch.uint8), drop_u=u, drop_p=p)
+    for name, got, leaf in zip(("dq", "dkin", "dval", "dWk", "dbk", "dWv", "dbv"), outs, leaves):
+        if name == "dbk":      # the key bias shifts every score of a row equally: its gradient is rounding noise around zero
+            assert (got - base).abs().max() < 1e-4 and leaf.grad.abs().max() < 1e-4
+            continue
+        assert _mr(got - base, leaf.grad) < 2e-4, (name, _mr(got - base, leaf.grad))
+
+
 @pytest.mark.parametrize("nq,N,masked", [(1, 400, False), (10, 100, True), (1, 20, True), (4, 20, False)])
 def test_native_decoder_stack_matches_op_by_op_path(lib, nq, N, masked):
     """DetrTransformerDecoder on the fused head kernels (one autograd node) against its own op-by-op PyTorch path (the

@@ -408,3 +408,26 @@ def test_token_branch_only_inference_skips_the_decoder():
     assert tok["decoder_branch_output"] == {"pred_logits": None, "pred_boxes": None} and tok["decoder_features"] is None
     assert torch.equal(tok["token_branch_output"]["pred_boxes"], full["token_branch_output"]["pred_boxes"])
     assert torch.equal(tok["token_branch_output"]["pred_logits"], full["token_branch_output"]["pred_logits"])
+
+
+def test_chunked_backward_plan_tiles_the_encoder_gradient_buffer():
+    """The multi-GPU graph runtime cuts the encoder backward into chunks of layers and all-reduces each chunk's flat gradient
+    range while the next chunk runs: the chunks must cover every layer exactly once, top-down, layer 0 last and alone, and
+    their ranges (plus the embedding / final-LN parameters that travel with layer 0) must tile the buffer without overlap."""
+    from simvg_b200.models.vis_encs.beit.beit3 import BEIT3, layer_flat_range
+    from simvg_b200.runtime import GraphedTrainStep
+    enc = BEIT3(img_size=64, patch_size=32, vit_type="base", vocab_size=32)
+    nl = enc.cfg["layers"]
+    fb = enc.flat()
+    for cl in (1, 2, 3, 5, 12):
+        step = GraphedTrainStep.__new__(GraphedTrainStep)
+        step.chunk_layers = cl
+        chunks = step._chunks(nl)
+        assert chunks[-1] == (0, 0) and chunks[0][0] == nl - 1
+        seen = [li for hi, lo in chunks for li in range(hi, lo - 1, -1)]
+        assert seen == list(range(nl - 1, -1, -1)), (cl, chunks)
+        ranges = [(layer_flat_range(enc, lo)[0], layer_flat_range(enc, hi)[1]) if lo > 0 else (0, layer_flat_range(enc, 0)[1])
+                  for hi, lo in chunks]
+        ranges.sort()
+        assert ranges[0][0] == 0 and ranges[-1][1] == fb.numel
+        assert all(a[1] == b[0] for a, b in zip(ranges[:-1], ranges[1:])), (cl, ranges)
