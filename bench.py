@@ -345,7 +345,8 @@ def run_ours(args, cfg_name):
     # exchange -> [clip + Adam graph] (no collective is captured; simvg_b200/runtime.py).
     if use_graph:
         from simvg_b200.runtime import GraphedTrainStep
-        gstep = GraphedTrainStep(model, opt, ddp if world > 1 else None, warmup=2)
+        gstep = GraphedTrainStep(model, opt, ddp if world > 1 else None, warmup=2,
+                                 chunk_layers=None if args.chunk_layers < 0 else args.chunk_layers)
 
     def graphed_step(d, metas):
         losses, _preds = gstep(d["img"], d["ref_expr_inds"], metas, d["text_attention_mask"], d["gt_box_t"])
@@ -470,6 +471,9 @@ def run_ours(args, cfg_name):
                    "operands": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LN / softmax / optimiser",
                    "launch": ("eager launches" if not graphed else
                               "whole step replayed as one CUDA graph (simvg_b200.runtime.GraphedTrainStep)" if world == 1 else
+                              "CUDA graphs per step: fwd+head-bwd | encoder backward in %d-layer chunks | clip+Adam; each chunk's "
+                              "gradient range is all-reduced (NCCL, asynchronous) under the following chunks"
+                              % (2 if args.chunk_layers < 0 else args.chunk_layers) if (args.chunk_layers != 0) else
                               "two CUDA graphs per step (fwd+bwd | clip+Adam) with the NCCL gradient exchange between them")},
         "clocks": clocks,
         "e2e": {"value": ips_e2e, "unit": "img/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": batch_bytes(kind),
@@ -502,6 +506,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=2, help="images per CPU-reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fp32-input", action="store_true", help="time value / e2e on the reference's float32 NCHW input instead of uint8 HWC")
+    ap.add_argument("--chunk-layers", type=int, default=-1,
+                    help="N > 1 graph runtime: encoder layers per backward chunk graph (0 = one backward graph, exchange after it)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch loop instead of the whole-step CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

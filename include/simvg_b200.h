@@ -287,6 +287,9 @@ typedef struct simvgb_head_xattn_args {
 long long simvgb_head_xattn_ws_floats(int B, int nq, int N, int backward);
 int simvgb_head_xattn(const simvgb_head_xattn_args* args, int backward, void* stream);
 
+/* TMA descriptor cache counters (descriptors are cached per (pointer, shape, stride, box); diagnostics / tests). */
+void simvgb_tmap_cache_stats(long long* hits, long long* misses);
+
 /* Hungarian matching on the device (detrex HungarianMatcher + scipy.optimize.linear_sum_assignment; called from
  * simvg/core/criterion/criterion.py:226-271).  cost: fp32 [B, nq, ttot], sample b's targets are columns
  * offsets[b] .. offsets[b+1]-1 (int32 [B+1], device); every sample needs nq <= 32 and <= 32 targets.  out_q / out_t: int64

@@ -4,6 +4,7 @@ PyTorch only owns memory and streams here; every function below launches hand-wr
 current stream and raises if the library or a CUDA device is missing (no CPU / eager fallback).
 """
 import ctypes
+import os
 
 import torch
 
@@ -36,11 +37,49 @@ def profile_stop():
     return out
 
 
+# NVTX ranges per fused op / per layer (SIMVGB_NVTX=1): visible in nsys / ncu --nvtx timelines; off by default (two host calls
+# per range).  The ranges follow the reference's module names so a timeline reads like the reference's forward.
+_nvtx_on = [os.environ.get("SIMVGB_NVTX", "0") not in ("", "0")]
+
+
+class nvtx:
+    """with K.nvtx("encoder.layer3.fwd"): ...   — no-op unless SIMVGB_NVTX=1 (or kernels.enable_nvtx())."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _nvtx_on[0]:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if _nvtx_on[0]:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
+def enable_nvtx(on=True):
+    _nvtx_on[0] = bool(on)
+
+
+def nvtx_push(name):
+    if _nvtx_on[0]:
+        torch.cuda.nvtx.range_push(name)
+
+
+def nvtx_pop():
+    if _nvtx_on[0]:
+        torch.cuda.nvtx.range_pop()
+
+
 class _timed:
     def __init__(self, family, flops):
         self.family, self.flops = family, flops
 
     def __enter__(self):
+        if _nvtx_on[0]:
+            torch.cuda.nvtx.range_push(self.family)
         if _prof[0] is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e0.record()
@@ -51,6 +90,8 @@ class _timed:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             _prof[0].setdefault(self.family, []).append((self.e0, e1, self.flops))
+        if _nvtx_on[0]:
+            torch.cuda.nvtx.range_pop()
         return False
 
 

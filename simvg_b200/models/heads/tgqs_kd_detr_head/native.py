@@ -218,7 +218,8 @@ def stack_backward(dec, ctx, dout):
 class _DecoderStackFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dec, query, qpos, kin, val, kpm, anchor):
-        out, saved = stack_forward(dec, query, qpos, kin, val, kpm, dec.training)
+        with K.nvtx("head.decoder.fwd"):
+            out, saved = stack_forward(dec, query, qpos, kin, val, kpm, dec.training)
         ctx.dec, ctx.saved = dec, saved
         return out
 
@@ -226,7 +227,7 @@ class _DecoderStackFn(torch.autograd.Function):
     def backward(ctx, dout):
         if ctx.saved is None:
             raise RuntimeError("decoder stack backward called twice")
-        with torch.no_grad():
+        with torch.no_grad(), K.nvtx("head.decoder.bwd"):
             dq, dqp, dkin, dval = stack_backward(ctx.dec, ctx.saved, dout)
         ctx.saved = None
         return None, dq, dqp, dkin, dval, None, torch.zeros(1, device=dout.device)

@@ -333,6 +333,7 @@ def encoder_forward(mod, image, ids, pad_mask, save):
     saved = []
     scale_q = (D // H) ** -0.5
     for li, pair in enumerate(layers):
+        K.nvtx_push("encoder.layers.%d.fwd" % li)
         dp1, dp2 = dps[li]
         dpv = (dp1, dp2)
         sv = [dict(), dict()]
@@ -374,6 +375,7 @@ def encoder_forward(mod, image, ids, pad_mask, save):
             x[g] = xn[g]
         if save:
             saved.append(dict(g=sv, lse=lse, dp=(dp1, dp2)))
+        K.nvtx_pop()
     outs, fin = [], []
     for g, which in enumerate(("A", "B")):
         y, mF, rF = K.ln_fwd(x[g], glob["fin_%s_w" % which][0], glob["fin_%s_b" % which][0], eps, out_dtype=f32)
@@ -438,6 +440,7 @@ class EncoderBackward:
         dres, dyb, fb, ddp = self.dres, self.dyb, self.fb, self.ddp
         nf = len(_GROUP_FIELDS)
         for li in range(hi, lo - 1, -1):
+            K.nvtx_push("encoder.layers.%d.bwd" % li)
             sl = ctx["layers"][li]
             dp1, _dp2 = sl["dp"]
             Gs = layers[li]
@@ -493,6 +496,7 @@ class EncoderBackward:
                 _zero_frozen(fb, i0, i1)   # BEFORE the range is handed to the (asynchronous, in-place) all-reduce
             if ddp is not None and li > 0:
                 ddp.on_encoder_range_done(fb.offsets[i0], fb.offsets[i1] if i1 < len(fb.offsets) else fb.numel)
+            K.nvtx_pop()
 
     def finish(self):
         mod, ctx, glob, dres, fb, ddp, dev = self.mod, self.ctx, self.glob, self.dres, self.fb, self.ddp, self.dev

@@ -173,6 +173,10 @@ class FusedAdamAMSGrad(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        with K.nvtx("optimizer.clip+adam_amsgrad"):
+            return self._step(loss)
+
+    def _step(self, loss):
         if self.graph_mode:
             self._step_graph()
             return loss

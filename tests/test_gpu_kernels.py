@@ -99,6 +99,42 @@ def test_gemm_epilogues(K):
     assert maxrel(o, prev + ref - bias) < 1e-5
 
 
+def test_tensor_map_cache_and_nvtx_ranges(K):
+    """TMA descriptors are cached on (pointer, shape, stride, box): a repeated launch on the same buffers re-encodes nothing and
+    computes the same result; a recycled pointer with another shape misses instead of reusing a stale descriptor.  NVTX ranges
+    (SIMVGB_NVTX / kernels.enable_nvtx) wrap launches without changing them."""
+    import ctypes
+    from simvg_b200 import _lib as L
+
+    def stats():
+        h, m = ctypes.c_longlong(), ctypes.c_longlong()
+        L.lib().simvgb_tmap_cache_stats(ctypes.byref(h), ctypes.byref(m))
+        return h.value, m.value
+
+    torch.manual_seed(2)
+    M, N, K_ = 512, 768, 768
+    X = torch.randn(M, K_, device=DEV).bfloat16()
+    W = (torch.randn(N, K_, device=DEV) * 0.05).bfloat16()
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    K.gemm(X, W, M, N, K_, epilogue=K.EPI_BF16, out=out)
+    first = out.clone()
+    h0, m0 = stats()
+    K.enable_nvtx(True)
+    try:
+        with K.nvtx("test.range"):
+            K.gemm(X, W, M, N, K_, epilogue=K.EPI_BF16, out=out)
+    finally:
+        K.enable_nvtx(False)
+    h1, m1 = stats()
+    assert h1 - h0 >= 2 and m1 == m0
+    assert torch.equal(out, first)
+    # same base pointers, half the rows: other descriptors, correct result
+    o2 = K.gemm(X[:256], W, 256, N, K_, epilogue=K.EPI_BF16, out=out[:256])
+    h2, m2 = stats()
+    assert m2 > m1
+    assert maxrel(o2, X[:256].float() @ W.float().t()) < 4e-3
+
+
 def test_gemm_full_size_identity_is_exact(K):
     """Size-independent property at the cfg2 problem size (M = 64*1601 rows): X @ I == X bit-for-bit."""
     M, D = 64 * 1601, 768

@@ -202,7 +202,7 @@ def _ddp_worker(rank, world, port, out):
     a = torch.cat([p.detach().flatten() for p, _ in keep])
     c = torch.cat([q.detach().flatten() for _, q in keep])
     res["graph_vs_eager_rel"] = float((a - c).norm() / a.norm())
-    res["graphs"] = step.graph_opt is not None
+    res["graphs"] = step.graph_opt is not None and len(step.plan) > 2     # backward cut into chunk graphs
     torch.save(res, os.path.join(out, "ddp%d.pt" % rank))
     dist.destroy_process_group()
 
@@ -437,9 +437,9 @@ def test_native_decoder_stack_matches_op_by_op_path(lib, nq, N, masked):
     assert o0.shape == o1.shape and _mr(o1, o0) < 2e-5
     assert _mr(dq1, dq0) < 2e-4 and _mr(dp1, dp0) < 2e-4 and _mr(dk1, dk0) < 2e-4
     for n in g0:
-        if g0[n].abs().max() < 1e-9:     # e.g. the self-attention q / k projections when nq = 1 (softmax over one key)
-            assert g1[n].abs().max() < 1e-6, n
-            continue
+        if g0[n].abs().max() < 1e-6:     # mathematically zero gradients (rounding noise on either path): the self-attention q / k
+            assert g1[n].abs().max() < 1e-6, n   # projections when nq = 1 (softmax over one key); all of layer 0's self-attention
+            continue                             # input projection here (content queries start at zero)
         assert _mr(g1[n], g0[n]) < 5e-4, (n, _mr(g1[n], g0[n]))
     # training mode (dropout on): finite outputs and gradients
     dec.use_native = True
