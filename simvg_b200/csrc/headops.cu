@@ -21,6 +21,53 @@ __device__ __forceinline__ float drop_scale(const float* __restrict__ u, long lo
   return (u == nullptr || p <= 0.f) ? 1.f : (u[idx] >= p ? 1.f / (1.f - p) : 0.f);
 }
 
+// ------------------------------------------------------------------------------------------------ small fp32 GEMM skeleton
+// The head's linears have R = B * nq (64 ... 640) rows: a launch is a handful of 32 x 32 output tiles and its time is the
+// latency of the contraction loop, not throughput.  One iteration therefore covers kD = 64 contraction steps, and the global
+// loads of iteration i + 1 are issued into registers before the FMAs of iteration i (the loop then costs ~max(load latency,
+// 64 FMA steps) instead of their sum per 32 steps).  la(i, c) / lb(j, c) fetch operand elements (zero outside the problem):
+// i / j index the tile's 32 output rows / columns, c the contraction.  *_CFAST says which index is contiguous in memory, so
+// that a warp's loads cover whole 128-byte lines either way; the smem tiles are contraction-major ([c][32 + 1]) for both.
+constexpr int kD = 64;
+
+template <bool A_CFAST, bool B_CFAST, bool ASUM, class LA, class LB>
+__device__ __forceinline__ void tile_gemm(int c_lo, int c_hi, LA la, LB lb, float (&acc)[2][2], float (&asum)[2]) {
+  __shared__ float As[kD][kT + 1], Bs[kD][kT + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 2 x 2 outputs each
+  float ra[8], rb[8];
+  auto fetch = [&](int c0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int e = threadIdx.x + 256 * q;
+      const int ia = A_CFAST ? e / kD : e % kT, ca = A_CFAST ? e % kD : e / kT;
+      const int ib = B_CFAST ? e / kD : e % kT, cb = B_CFAST ? e % kD : e / kT;
+      ra[q] = c0 + ca < c_hi ? la(ia, c0 + ca) : 0.f;
+      rb[q] = c0 + cb < c_hi ? lb(ib, c0 + cb) : 0.f;
+    }
+  };
+  if (c_lo < c_hi) fetch(c_lo);
+  for (int c0 = c_lo; c0 < c_hi; c0 += kD) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int e = threadIdx.x + 256 * q;
+      const int ia = A_CFAST ? e / kD : e % kT, ca = A_CFAST ? e % kD : e / kT;
+      const int ib = B_CFAST ? e / kD : e % kT, cb = B_CFAST ? e % kD : e / kT;
+      As[ca][ia] = ra[q];
+      Bs[cb][ib] = rb[q];
+    }
+    __syncthreads();
+    if (c0 + kD < c_hi) fetch(c0 + kD);
+#pragma unroll 16
+    for (int c = 0; c < kD; ++c) {
+      const float a0 = As[c][ty], a1 = As[c][ty + 16], b0 = Bs[c][tx], b1 = Bs[c][tx + 16];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+      if (ASUM) { asum[0] += a0; asum[1] += a1; }
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ linear forward
 // y[r, n] = epi( sum_k (x[r,k] + (n < n_split ? x2[r,k] : 0)) * W[n,k] + b[n] ),  epi = [ReLU] then [dropout]
 // split-K (gridDim.z > 1): partial sums are atomically added into y (zeroed by the caller), bias from split 0; no epilogue.
@@ -32,36 +79,22 @@ struct LinFwd {
 };
 
 __global__ void __launch_bounds__(256) lin_fwd_kernel(const LinFwd p) {
-  __shared__ float As[kT][kT + 1], Bs[kT][kT + 1];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 2 x 2 outputs each
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int n0 = blockIdx.x * kT, r0 = blockIdx.y * kT;
   const int ks = gridDim.z, kz = blockIdx.z;
-  const int kchunk = ((p.K + ks - 1) / ks + kT - 1) / kT * kT;
+  const int kchunk = ((p.K + ks - 1) / ks + kD - 1) / kD * kD;
   const int k_lo = kz * kchunk, k_hi = min(p.K, k_lo + kchunk);
   const bool add2 = p.x2 != nullptr && n0 < p.n_split;
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int k0 = k_lo; k0 < k_hi; k0 += kT) {
-    for (int i = threadIdx.x; i < kT * kT; i += 256) {
-      const int rr = i / kT, kk = i % kT;
-      const int r = r0 + rr, k = k0 + kk, n = n0 + rr;
-      float a = 0.f, w = 0.f;
-      if (r < p.R && k < k_hi) {
-        a = p.x[(long long)r * p.K + k];
-        if (add2) a += p.x2[(long long)r * p.K + k];
-      }
-      if (n < p.N && k < k_hi) w = p.W[(long long)n * p.K + k];
-      As[rr][kk] = a;
-      Bs[rr][kk] = w;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int kk = 0; kk < kT; ++kk) {
-      const float a0 = As[ty][kk], a1 = As[ty + 16][kk], b0 = Bs[tx][kk], b1 = Bs[tx + 16][kk];
-      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
-      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
-    }
-    __syncthreads();
-  }
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, unused[2];
+  auto la = [&](int i, int k) {
+    const int r = r0 + i;
+    if (r >= p.R) return 0.f;
+    float a = p.x[(long long)r * p.K + k];
+    if (add2) a += p.x2[(long long)r * p.K + k];
+    return a;
+  };
+  auto lb = [&](int j, int k) { return n0 + j < p.N ? p.W[(long long)(n0 + j) * p.K + k] : 0.f; };
+  tile_gemm<true, true, false>(k_lo, k_hi, la, lb, acc, unused);
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -98,33 +131,18 @@ __device__ __forceinline__ float lin_dye(const LinBwd& p, int r, int n) {
   return g;
 }
 
-// dx[r,k] += sum_{n in [n_lo, n_hi)} dye[r,n] W[n,k]   (also into dx2 when given); contraction split over gridDim.z, atomics
+// dx[r,k] += sum_{n in [n_lo, n_hi)} dye[r,n] W[n,k]   (also into dx2 when given); contraction split over gridDim.z (atomics then)
 __global__ void __launch_bounds__(256) lin_bwd_x_kernel(const LinBwd p) {
-  __shared__ float As[kT][kT + 1], Bs[kT][kT + 1];   // As[r][n], Bs[n][k]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int k0 = blockIdx.x * kT, r0 = blockIdx.y * kT;
   const int ns = gridDim.z, nz = blockIdx.z;
   const int span = p.n_hi - p.n_lo;
-  const int nchunk = ((span + ns - 1) / ns + kT - 1) / kT * kT;
+  const int nchunk = ((span + ns - 1) / ns + kD - 1) / kD * kD;
   const int lo = p.n_lo + nz * nchunk, hi = min(p.n_hi, lo + nchunk);
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int n0 = lo; n0 < hi; n0 += kT) {
-    for (int i = threadIdx.x; i < kT * kT; i += 256) {
-      const int a = i / kT, c = i % kT;
-      const int r = r0 + a, n = n0 + c;
-      As[a][c] = (r < p.R && n < hi) ? lin_dye(p, r, n) : 0.f;
-      const int nn = n0 + a, k = k0 + c;
-      Bs[a][c] = (nn < hi && k < p.K) ? p.W[(long long)nn * p.K + k] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int nn = 0; nn < kT; ++nn) {
-      const float a0 = As[ty][nn], a1 = As[ty + 16][nn], b0 = Bs[nn][tx], b1 = Bs[nn][tx + 16];
-      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
-      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
-    }
-    __syncthreads();
-  }
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, unused[2];
+  auto la = [&](int i, int n) { return r0 + i < p.R ? lin_dye(p, r0 + i, n) : 0.f; };
+  auto lb = [&](int j, int n) { return k0 + j < p.K ? p.W[(long long)n * p.K + k0 + j] : 0.f; };
+  tile_gemm<true, false, false>(lo, hi, la, lb, acc, unused);
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -132,42 +150,31 @@ __global__ void __launch_bounds__(256) lin_bwd_x_kernel(const LinBwd p) {
       const int r = r0 + ty + 16 * i, k = k0 + tx + 16 * j;
       if (r >= p.R || k >= p.K) continue;
       const long long o = (long long)r * p.K + k;
-      if (p.dx != nullptr) atomicAdd(p.dx + o, acc[i][j]);
-      if (p.dx2 != nullptr) atomicAdd(p.dx2 + o, acc[i][j]);
+      if (ns > 1) {
+        if (p.dx != nullptr) atomicAdd(p.dx + o, acc[i][j]);
+        if (p.dx2 != nullptr) atomicAdd(p.dx2 + o, acc[i][j]);
+      } else {       // the tile has one owner: plain accumulate, deterministic
+        if (p.dx != nullptr) p.dx[o] += acc[i][j];
+        if (p.dx2 != nullptr) p.dx2[o] += acc[i][j];
+      }
     }
 }
 
 // dW[n,k] += sum_r dye[r,n] (x[r,k] + (n < n_split ? x2[r,k] : 0));  db[n] += sum_r dye[r,n]   (k-tile 0 only)
 __global__ void __launch_bounds__(256) lin_bwd_w_kernel(const LinBwd p) {
-  __shared__ float As[kT][kT + 1], Bs[kT][kT + 1];   // As[r][n], Bs[r][k]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int k0 = blockIdx.x * kT, n0 = blockIdx.y * kT;
   const bool add2 = p.x2 != nullptr && n0 < p.n_split;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   float bsum[2] = {0.f, 0.f};
-  for (int r0 = 0; r0 < p.R; r0 += kT) {
-    for (int i = threadIdx.x; i < kT * kT; i += 256) {
-      const int a = i / kT, c = i % kT;
-      const int r = r0 + a;
-      const int n = n0 + c, k = k0 + c;
-      As[a][c] = (r < p.R && n < p.N) ? lin_dye(p, r, n) : 0.f;
-      float xv = 0.f;
-      if (r < p.R && k < p.K) {
-        xv = p.x[(long long)r * p.K + k];
-        if (add2) xv += p.x2[(long long)r * p.K + k];
-      }
-      Bs[a][c] = xv;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int rr = 0; rr < kT; ++rr) {
-      const float a0 = As[rr][ty], a1 = As[rr][ty + 16], b0 = Bs[rr][tx], b1 = Bs[rr][tx + 16];
-      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
-      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
-      if (tx == 0) { bsum[0] += a0; bsum[1] += a1; }
-    }
-    __syncthreads();
-  }
+  auto la = [&](int i, int r) { return n0 + i < p.N ? lin_dye(p, r, n0 + i) : 0.f; };
+  auto lb = [&](int j, int r) {
+    if (k0 + j >= p.K) return 0.f;
+    float xv = p.x[(long long)r * p.K + k0 + j];
+    if (add2) xv += p.x2[(long long)r * p.K + k0 + j];
+    return xv;
+  };
+  tile_gemm<false, false, true>(0, p.R, la, lb, acc, bsum);
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int n = n0 + ty + 16 * i;
@@ -589,9 +596,13 @@ __global__ void __launch_bounds__(256) xattn_bwd_kv_kernel(const float* __restri
   float ok[XK], ov[XK];
 #pragma unroll
   for (int k = 0; k < XK; ++k) { ok[k] = 0.f; ov[k] = 0.f; }
+  float un = u[(long long)b * IH * XE + e], zn = dz[(long long)b * IH * XE + e];
   for (int ih = 0; ih < IH; ++ih) {
-    const float uu = u[((long long)b * IH + ih) * XE + e];
-    const float zz = dz[((long long)b * IH + ih) * XE + e];
+    const float uu = un, zz = zn;
+    if (ih + 1 < IH) {                 // next row's operands in flight under this row's FMAs
+      un = u[((long long)b * IH + ih + 1) * XE + e];
+      zn = dz[((long long)b * IH + ih + 1) * XE + e];
+    }
 #pragma unroll
     for (int k = 0; k < XK; k += 4) {
       const float4 a4 = *reinterpret_cast<const float4*>(ds_s + ih * XK + k);

@@ -277,8 +277,14 @@ class _LinearFn(torch.autograd.Function):
         return dx, None, None, torch.zeros(1, device=dy.device)
 
 
+_linear_native = [True]    # tests / diagnostics: False routes head linears through torch's op-by-op path (the kernels' reference)
+
+
 def linear(lin, x, relu=False):
     """nn.Linear `lin` (+ optional ReLU) applied to x [..., K] on the native head kernels (CUDA fp32 tensors)."""
+    if not _linear_native[0]:
+        y = lin(x)
+        return torch.relu(y) if relu else y
     lead = x.shape[:-1]
     x2d = x.reshape(-1, x.shape[-1]).contiguous().float()
     if torch.is_grad_enabled() and (x2d.requires_grad or lin.weight.requires_grad):
