@@ -5,3 +5,4 @@ from .builder import (FUSIONS, HEADS, LAN_ENCODERS, MODELS, VIS_ENCODERS, build_
 from .det_seg import *  # noqa: F401,F403
 from .heads import *  # noqa: F401,F403
 from .vis_encs import *  # noqa: F401,F403
+from .utils import ExponentialMovingAverage  # noqa: F401,E402

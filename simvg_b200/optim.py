@@ -113,6 +113,18 @@ class FusedAdamAMSGrad(torch.optim.Optimizer):
         t = self.ema_t if t is None else t
         return min(self.ema_alpha, (t + 1.0) / (t + 10.0))       # models/utils.py:149
 
+    def swap_ema(self):
+        """Exchange the live parameters with their averages in place (evaluation with the EMA weights: the reference's
+        `model_ema.apply_shadow()` ... `model_ema.restore()`, tools/train.py:133-138); call again to swap back.  The bf16 operand
+        shadows of the encoder follow the parameters on its next forward (it re-casts from the flat buffer every call)."""
+        if self.ema_alpha is None:
+            raise RuntimeError("EMA is not enabled (ema_alpha=None)")
+        with torch.no_grad():
+            for s in self.segments:
+                tmp = s.fb.data.clone()
+                s.fb.data.copy_(s.ema)
+                s.ema.copy_(tmp)
+
     def ema_view(self, p):
         """The EMA shadow of parameter `p` (a view of the flat shadow buffer)."""
         s, i = self._where[id(p)]

@@ -113,3 +113,50 @@ def test_ema_decay_schedule_and_views():
     assert opt.ema_decay(100000) == 0.999
     p = model.head.query_embed.weight
     assert torch.equal(opt.ema_view(p), p.detach()) and opt.ema_view(p).data_ptr() != p.data_ptr()
+
+
+def test_exponential_moving_average_has_the_reference_interface():
+    """simvg/models/utils.py:130-180: update_params() (decay = min(alpha, (1 + step) / (10 + step))), apply_shadow() / restore()
+    around evaluation, `shadow` for the checkpoint — standalone (any optimiser) and backed by the fused optimiser's flat EMA
+    stream (swap of two buffers instead of state-dict clones)."""
+    from simvg_b200.models import ExponentialMovingAverage
+    from simvg_b200.optim import FusedAdamAMSGrad
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 2))
+    ema = ExponentialMovingAverage(model, 0.9)
+    want = {k: v.detach().clone() for k, v in model.named_parameters()}
+    for step in range(4):
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(torch.randn_like(p) * 0.1)
+        decay = min(0.9, (step + 1) / (step + 10))
+        for k, p in model.named_parameters():
+            want[k] = decay * want[k] + (1 - decay) * p.detach()
+        ema.update_params()
+    assert ema.step == 4
+    live = {k: v.detach().clone() for k, v in model.named_parameters()}
+    for k, v in ema.shadow.items():
+        assert torch.allclose(v, want[k], atol=1e-6)
+    ema.apply_shadow()
+    for k, p in model.named_parameters():
+        assert torch.allclose(p, want[k], atol=1e-6)
+    with pytest.raises(RuntimeError):
+        ema.apply_shadow()
+    ema.restore()
+    for k, p in model.named_parameters():
+        assert torch.equal(p, live[k])
+    # backed by the fused optimiser: the average lives in its flat buffers; apply / restore swap in place
+    opt = FusedAdamAMSGrad(model, lr=1e-3)
+    ema2 = ExponentialMovingAverage(model, 0.999, optimizer=opt)
+    assert opt.ema_alpha == 0.999
+    p0 = next(model.parameters())
+    with torch.no_grad():
+        opt.ema_view(p0).add_(1.0)
+    before = p0.detach().clone()
+    ema2.apply_shadow()
+    assert torch.allclose(p0, before + 1.0)
+    assert torch.allclose(opt.ema_view(p0), before)
+    ema2.restore()
+    assert torch.equal(p0, before)
+    ema2.load_shadow({k: torch.zeros_like(v) for k, v in model.named_parameters()})
+    assert float(opt.ema_view(p0).abs().max()) == 0.0
