@@ -24,25 +24,36 @@ __device__ __forceinline__ float drop_scale(const float* __restrict__ u, long lo
 // ------------------------------------------------------------------------------------------------ small fp32 GEMM skeleton
 // The head's linears have R = B * nq (64 ... 640) rows: a launch is a handful of 32 x 32 output tiles and its time is the
 // latency of the contraction loop, not throughput.  One iteration therefore covers kD = 64 contraction steps, and the global
-// loads of iteration i + 1 are issued into registers before the FMAs of iteration i (the loop then costs ~max(load latency,
-// 64 FMA steps) instead of their sum per 32 steps).  la(i, c) / lb(j, c) fetch operand elements (zero outside the problem):
-// i / j index the tile's 32 output rows / columns, c the contraction.  *_CFAST says which index is contiguous in memory, so
-// that a warp's loads cover whole 128-byte lines either way; the smem tiles are contraction-major ([c][32 + 1]) for both.
+// loads of iteration i + 1 are issued into registers before the FMAs of iteration i.  The fetch stage ONLY loads: a warp issues
+// in order and stalls at the first use of a loaded register, so any arithmetic on an operand element (the position add, the
+// ReLU / dropout mask of the backward) placed next to its load would serialise the eight loads of a thread into eight L2 round
+// trips (measured: 3 us per iteration, 4.5 x slower than cuBLAS at K = 2048).  la(i, c) / lb(j, c) return the RAW loaded words
+// of an operand element (zero-initialised struct outside the problem), ca / cb turn them into the operand value when the tile is
+// written to shared memory.  i / j index the tile's 32 output rows / columns, c the contraction; *_CFAST says which index is
+// contiguous in memory, so that a warp's loads cover whole 128-byte lines either way; the smem tiles are contraction-major.
 constexpr int kD = 64;
 
-template <bool A_CFAST, bool B_CFAST, bool ASUM, class LA, class LB>
-__device__ __forceinline__ void tile_gemm(int c_lo, int c_hi, LA la, LB lb, float (&acc)[2][2], float (&asum)[2]) {
+struct Raw1 { float a; };
+struct Raw2 { float a, b; };
+struct Raw3 { float a, b, c; };
+
+template <bool A_CFAST, bool B_CFAST, bool ASUM, class RA, class RB, class LA, class LB, class CA, class CB>
+__device__ __forceinline__ void tile_gemm(int c_lo, int c_hi, LA la, LB lb, CA ca_fn, CB cb_fn, float (&acc)[2][2],
+                                          float (&asum)[2]) {
   __shared__ float As[kD][kT + 1], Bs[kD][kT + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 2 x 2 outputs each
-  float ra[8], rb[8];
+  RA ra[8];
+  RB rb[8];
   auto fetch = [&](int c0) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int e = threadIdx.x + 256 * q;
       const int ia = A_CFAST ? e / kD : e % kT, ca = A_CFAST ? e % kD : e / kT;
       const int ib = B_CFAST ? e / kD : e % kT, cb = B_CFAST ? e % kD : e / kT;
-      ra[q] = c0 + ca < c_hi ? la(ia, c0 + ca) : 0.f;
-      rb[q] = c0 + cb < c_hi ? lb(ib, c0 + cb) : 0.f;
+      ra[q] = RA{};
+      rb[q] = RB{};
+      if (c0 + ca < c_hi) ra[q] = la(ia, c0 + ca);
+      if (c0 + cb < c_hi) rb[q] = lb(ib, c0 + cb);
     }
   };
   if (c_lo < c_hi) fetch(c_lo);
@@ -52,8 +63,8 @@ __device__ __forceinline__ void tile_gemm(int c_lo, int c_hi, LA la, LB lb, floa
       const int e = threadIdx.x + 256 * q;
       const int ia = A_CFAST ? e / kD : e % kT, ca = A_CFAST ? e % kD : e / kT;
       const int ib = B_CFAST ? e / kD : e % kT, cb = B_CFAST ? e % kD : e / kT;
-      As[ca][ia] = ra[q];
-      Bs[cb][ib] = rb[q];
+      As[ca][ia] = ca_fn(ra[q]);
+      Bs[cb][ib] = cb_fn(rb[q]);
     }
     __syncthreads();
     if (c0 + kD < c_hi) fetch(c0 + kD);
@@ -87,14 +98,21 @@ __global__ void __launch_bounds__(256) lin_fwd_kernel(const LinFwd p) {
   const bool add2 = p.x2 != nullptr && n0 < p.n_split;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, unused[2];
   auto la = [&](int i, int k) {
+    Raw2 v{0.f, 0.f};
     const int r = r0 + i;
-    if (r >= p.R) return 0.f;
-    float a = p.x[(long long)r * p.K + k];
-    if (add2) a += p.x2[(long long)r * p.K + k];
-    return a;
+    if (r < p.R) {
+      v.a = p.x[(long long)r * p.K + k];
+      if (add2) v.b = p.x2[(long long)r * p.K + k];
+    }
+    return v;
   };
-  auto lb = [&](int j, int k) { return n0 + j < p.N ? p.W[(long long)(n0 + j) * p.K + k] : 0.f; };
-  tile_gemm<true, true, false>(k_lo, k_hi, la, lb, acc, unused);
+  auto lb = [&](int j, int k) {
+    Raw1 v{0.f};
+    if (n0 + j < p.N) v.a = p.W[(long long)(n0 + j) * p.K + k];
+    return v;
+  };
+  tile_gemm<true, true, false, Raw2, Raw1>(k_lo, k_hi, la, lb, [](const Raw2& v) { return v.a + v.b; },
+                                           [](const Raw1& v) { return v.a; }, acc, unused);
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -124,11 +142,28 @@ struct LinBwd {
   float drop_p;
 };
 
-__device__ __forceinline__ float lin_dye(const LinBwd& p, int r, int n) {
+// raw words of one dye element: dy, the dropout uniform (1 = keep when there is no dropout), the forward output (1 when no ReLU)
+__device__ __forceinline__ Raw3 dye_load(const LinBwd& p, int r, int n) {
   const long long o = (long long)r * p.N + n;
-  float g = p.dy[o] * drop_scale(p.drop_u, o, p.drop_p);
-  if (p.relu && !(p.y[o] > 0.f)) g = 0.f;
-  return g;
+  Raw3 v{p.dy[o], 1.f, 1.f};
+  if (p.drop_u != nullptr && p.drop_p > 0.f) v.b = p.drop_u[o];
+  if (p.relu) v.c = p.y[o];
+  return v;
+}
+
+struct DyeCook {
+  float drop_p, keep;
+  bool drop;
+  __device__ __forceinline__ float operator()(const Raw3& v) const {
+    float g = v.a;
+    if (drop) g *= (v.b >= drop_p ? keep : 0.f);
+    return v.c > 0.f ? g : 0.f;
+  }
+};
+
+__device__ __forceinline__ DyeCook dye_cook(const LinBwd& p) {
+  const bool drop = p.drop_u != nullptr && p.drop_p > 0.f;
+  return DyeCook{p.drop_p, drop ? 1.f / (1.f - p.drop_p) : 1.f, drop};
 }
 
 // dx[r,k] += sum_{n in [n_lo, n_hi)} dye[r,n] W[n,k]   (also into dx2 when given); contraction split over gridDim.z (atomics then)
@@ -140,9 +175,13 @@ __global__ void __launch_bounds__(256) lin_bwd_x_kernel(const LinBwd p) {
   const int nchunk = ((span + ns - 1) / ns + kD - 1) / kD * kD;
   const int lo = p.n_lo + nz * nchunk, hi = min(p.n_hi, lo + nchunk);
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, unused[2];
-  auto la = [&](int i, int n) { return r0 + i < p.R ? lin_dye(p, r0 + i, n) : 0.f; };
-  auto lb = [&](int j, int n) { return k0 + j < p.K ? p.W[(long long)n * p.K + k0 + j] : 0.f; };
-  tile_gemm<true, false, false>(lo, hi, la, lb, acc, unused);
+  auto la = [&](int i, int n) { return r0 + i < p.R ? dye_load(p, r0 + i, n) : Raw3{0.f, 1.f, 1.f}; };
+  auto lb = [&](int j, int n) {
+    Raw1 v{0.f};
+    if (k0 + j < p.K) v.a = p.W[(long long)n * p.K + k0 + j];
+    return v;
+  };
+  tile_gemm<true, false, false, Raw3, Raw1>(lo, hi, la, lb, dye_cook(p), [](const Raw1& v) { return v.a; }, acc, unused);
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -161,20 +200,26 @@ __global__ void __launch_bounds__(256) lin_bwd_x_kernel(const LinBwd p) {
 }
 
 // dW[n,k] += sum_r dye[r,n] (x[r,k] + (n < n_split ? x2[r,k] : 0));  db[n] += sum_r dye[r,n]   (k-tile 0 only)
+// The row contraction may be split over gridDim.z (many-row problems such as the text projection): atomics then.
 __global__ void __launch_bounds__(256) lin_bwd_w_kernel(const LinBwd p) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int k0 = blockIdx.x * kT, n0 = blockIdx.y * kT;
+  const int rs = gridDim.z, rz = blockIdx.z;
+  const int rchunk = ((p.R + rs - 1) / rs + kD - 1) / kD * kD;
+  const int r_lo = rz * rchunk, r_hi = min(p.R, r_lo + rchunk);
   const bool add2 = p.x2 != nullptr && n0 < p.n_split;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   float bsum[2] = {0.f, 0.f};
-  auto la = [&](int i, int r) { return n0 + i < p.N ? lin_dye(p, r, n0 + i) : 0.f; };
+  auto la = [&](int i, int r) { return n0 + i < p.N ? dye_load(p, r, n0 + i) : Raw3{0.f, 1.f, 1.f}; };
   auto lb = [&](int j, int r) {
-    if (k0 + j >= p.K) return 0.f;
-    float xv = p.x[(long long)r * p.K + k0 + j];
-    if (add2) xv += p.x2[(long long)r * p.K + k0 + j];
-    return xv;
+    Raw2 v{0.f, 0.f};
+    if (k0 + j < p.K) {
+      v.a = p.x[(long long)r * p.K + k0 + j];
+      if (add2) v.b = p.x2[(long long)r * p.K + k0 + j];
+    }
+    return v;
   };
-  tile_gemm<false, false, true>(0, p.R, la, lb, acc, bsum);
+  tile_gemm<false, false, true, Raw3, Raw2>(r_lo, r_hi, la, lb, dye_cook(p), [](const Raw2& v) { return v.a + v.b; }, acc, bsum);
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int n = n0 + ty + 16 * i;
@@ -182,9 +227,15 @@ __global__ void __launch_bounds__(256) lin_bwd_w_kernel(const LinBwd p) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int k = k0 + tx + 16 * j;
-      if (k < p.K) p.dW[(long long)n * p.K + k] += acc[i][j];      // each (n, k) belongs to exactly one thread of one block
+      if (k >= p.K) continue;
+      float* dst = p.dW + (long long)n * p.K + k;
+      if (rs > 1) atomicAdd(dst, acc[i][j]);
+      else *dst += acc[i][j];                                       // each (n, k) belongs to exactly one thread of one block
     }
-    if (tx == 0 && blockIdx.x == 0 && p.db != nullptr) p.db[n] += bsum[i];
+    if (tx == 0 && blockIdx.x == 0 && p.db != nullptr) {
+      if (rs > 1) atomicAdd(p.db + n, bsum[i]);
+      else p.db[n] += bsum[i];
+    }
   }
 }
 
@@ -197,33 +248,39 @@ struct LnRes {
   float drop_p, eps;
 };
 
+// PER = C / 32 is a template parameter: the per-row loops unroll completely, so a lane's loads are all in flight before the
+// first use (with a run-time trip count every 32 columns cost their own L2 round trip).
+template <int PER>
 __global__ void __launch_bounds__(128) lnres_fwd_kernel(const LnRes p) {
   const int lane = threadIdx.x & 31, row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= p.R) return;
-  const int per = p.C / 32;          // <= 16
-  float s[16];
+  constexpr int per = PER;
+  float s[PER], bv[PER], uv[PER];
+  const bool has_b = p.b != nullptr, drop = p.drop_u != nullptr && p.drop_p > 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const long long o = (long long)row * p.C + lane + 32 * i;
+    s[i] = p.a[o];
+    bv[i] = has_b ? p.b[o] : 0.f;
+    uv[i] = drop ? p.drop_u[o] : 1.f;
+  }
+  const float keep = drop ? 1.f / (1.f - p.drop_p) : 1.f;
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    if (i >= per) break;
-    const long long o = (long long)row * p.C + lane + 32 * i;
-    float v = p.a[o];
-    if (p.b != nullptr) v += p.b[o] * drop_scale(p.drop_u, o, p.drop_p);
-    s[i] = v;
-    sum += v;
+  for (int i = 0; i < PER; ++i) {
+    s[i] += bv[i] * ((!drop || uv[i] >= p.drop_p) ? keep : 0.f);
+    sum += s[i];
   }
   const float mu = warp_sum(sum) / p.C;
   float var = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    if (i >= per) break;
+  for (int i = 0; i < per; ++i) {
     const float d = s[i] - mu;
     var += d * d;
   }
   const float rs = rsqrtf(warp_sum(var) / p.C + p.eps);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    if (i >= per) break;
+  for (int i = 0; i < per; ++i) {
     const int c = lane + 32 * i;
     p.y[(long long)row * p.C + c] = (s[i] - mu) * rs * p.gamma[c] + p.beta[c];
   }
@@ -231,39 +288,48 @@ __global__ void __launch_bounds__(128) lnres_fwd_kernel(const LnRes p) {
 }
 
 // ds = LN'(dy);  da += ds;  db += ds * dropmask;  dgamma += sum_r dy * xhat;  dbeta += sum_r dy
+template <int PER>
 __global__ void __launch_bounds__(128) lnres_bwd_kernel(const LnRes p) {
   __shared__ float sg[512], sb[512];
   for (int i = threadIdx.x; i < p.C; i += 128) { sg[i] = 0.f; sb[i] = 0.f; }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int per = p.C / 32;
+  const bool has_b = p.b != nullptr, drop = p.drop_u != nullptr && p.drop_p > 0.f;
+  const float keep = drop ? 1.f / (1.f - p.drop_p) : 1.f;
   for (int row = blockIdx.x * 4 + (threadIdx.x >> 5); row < p.R; row += gridDim.x * 4) {
     const float mu = p.mean_in[row], rs = p.rstd_in[row];
-    float xh[16], g[16];
-    float s1 = 0.f, s2 = 0.f;
+    float xh[PER], g[PER], bv[PER], m[PER], d[PER], gam[PER], da0[PER], db0[PER];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      if (i >= per) break;
+    for (int i = 0; i < PER; ++i) {                      // loads only
       const int c = lane + 32 * i;
       const long long o = (long long)row * p.C + c;
-      float v = p.a[o];
-      if (p.b != nullptr) v += p.b[o] * drop_scale(p.drop_u, o, p.drop_p);
-      xh[i] = (v - mu) * rs;
-      const float d = p.dy[o];
-      atomicAdd(&sg[c], d * xh[i]);
-      atomicAdd(&sb[c], d);
-      g[i] = d * p.gamma[c];
+      xh[i] = p.a[o];
+      bv[i] = has_b ? p.b[o] : 0.f;
+      m[i] = drop ? p.drop_u[o] : 1.f;
+      d[i] = p.dy[o];
+      gam[i] = p.gamma[c];
+      da0[i] = p.da != nullptr ? p.da[o] : 0.f;
+      db0[i] = p.db != nullptr ? p.db[o] : 0.f;
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int c = lane + 32 * i;
+      m[i] = (!drop || m[i] >= p.drop_p) ? keep : 0.f;
+      xh[i] = (xh[i] + bv[i] * m[i] - mu) * rs;
+      atomicAdd(&sg[c], d[i] * xh[i]);
+      atomicAdd(&sb[c], d[i]);
+      g[i] = d[i] * gam[i];
       s1 += g[i];
       s2 += g[i] * xh[i];
     }
     const float c1 = warp_sum(s1) / p.C, c2 = warp_sum(s2) / p.C;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      if (i >= per) break;
+    for (int i = 0; i < PER; ++i) {
       const long long o = (long long)row * p.C + lane + 32 * i;
       const float ds = rs * (g[i] - c1 - xh[i] * c2);
-      if (p.da != nullptr) p.da[o] += ds;
-      if (p.db != nullptr) p.db[o] += ds * drop_scale(p.drop_u, o, p.drop_p);
+      if (p.da != nullptr) p.da[o] = da0[i] + ds;
+      if (p.db != nullptr) p.db[o] = db0[i] + ds * m[i];
     }
   }
   __syncthreads();
@@ -376,9 +442,12 @@ __global__ void __launch_bounds__(256) xattn_absorb_kernel(const float* __restri
   __syncthreads();
 #pragma unroll
   for (int h = 0; h < XH; ++h) {
+    float wv[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) wv[d] = W[(long long)(h * 32 + d) * XE + e];      // 32 loads in flight, then the FMAs
     float acc = 0.f;
-#pragma unroll 8
-    for (int d = 0; d < 32; ++d) acc = fmaf(xs[h * 32 + d], W[(long long)(h * 32 + d) * XE + e], acc);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) acc = fmaf(xs[h * 32 + d], wv[d], acc);
     u[((long long)r * XH + h) * XE + e] = acc;
   }
   const int warp = e >> 5, lane = e & 31;
@@ -715,24 +784,30 @@ extern "C" int simvgb_head_lin_bwd(const simvgb_head_lin_args* a, void* stream) 
       lin_bwd_x_kernel<<<dim3(kt, rt, ns), 256, 0, S(stream)>>>(ps);
     }
   }
-  if (a->dW != nullptr) lin_bwd_w_kernel<<<dim3(kt, nt), 256, 0, S(stream)>>>(p);
+  if (a->dW != nullptr) {
+    int rs = a->R >= 1024 ? a->R / 256 : 1;   // many-row problems (text projection: B * Lt rows) split the row contraction
+    if (rs > 8) rs = 8;
+    lin_bwd_w_kernel<<<dim3(kt, nt, rs), 256, 0, S(stream)>>>(p);
+  }
   SIMVGB_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int simvgb_head_lnres(const simvgb_head_ln_args* a, int backward, void* stream) {
   SIMVGB_CHECK(a && a->a && a->gamma, "simvgb_head_lnres: null pointer");
-  SIMVGB_CHECK(a->R > 0 && a->C % 32 == 0 && a->C <= 512, "simvgb_head_lnres: C must be a multiple of 32 and <= 512 (got %d)", a->C);
+  SIMVGB_CHECK(a->R > 0 && (a->C == 256 || a->C == 512), "simvgb_head_lnres: C must be 256 or 512 (got %d)", a->C);
   LnRes p{a->a, a->b, a->drop_u, a->gamma, a->beta, a->dy, a->mean, a->rstd, a->y, a->mean, a->rstd, a->da, a->db, a->dgamma, a->dbeta,
           a->R, a->C, a->drop_p, a->eps};
   if (!backward) {
     SIMVGB_CHECK(a->y && a->beta && a->mean && a->rstd, "simvgb_head_lnres: forward needs y, beta, mean, rstd");
-    lnres_fwd_kernel<<<(a->R + 3) / 4, 128, 0, S(stream)>>>(p);
+    if (a->C == 256) lnres_fwd_kernel<8><<<(a->R + 3) / 4, 128, 0, S(stream)>>>(p);
+    else lnres_fwd_kernel<16><<<(a->R + 3) / 4, 128, 0, S(stream)>>>(p);
   } else {
     SIMVGB_CHECK(a->dy && a->mean && a->rstd && a->dgamma && a->dbeta, "simvgb_head_lnres: backward needs dy, mean, rstd, dgamma, dbeta");
     int blocks = (a->R + 3) / 4;
     if (blocks > 64) blocks = 64;
-    lnres_bwd_kernel<<<blocks, 128, 0, S(stream)>>>(p);
+    if (a->C == 256) lnres_bwd_kernel<8><<<blocks, 128, 0, S(stream)>>>(p);
+    else lnres_bwd_kernel<16><<<blocks, 128, 0, S(stream)>>>(p);
   }
   SIMVGB_CUDA(cudaGetLastError());
   return 0;

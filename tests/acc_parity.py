@@ -64,8 +64,43 @@ def accuracy_at_05(pred, gt_list):
     return ((inter / (a1 + a2 - inter).clamp(min=1e-6)) >= 0.5).float().mean() * 100.0
 
 
-def run(steps=1500, B=32, S=128, layers=2, P=16, n_eval=8, log_every=100, out_path="gpurun_out/acc_parity.json"):
+class _RefArm:
+    """One reference arm: the oracle's arithmetic (fp32, or with the product's bf16 operand roundings emulated) trained with
+    torch Adam(amsgrad) over the reference's lr groups + clip_grad_norm_ + the shared step schedule."""
+
+    def __init__(self, cls, sd0, cfg, S, P, layers, steps, dev):
+        self.sd = {k: v.clone().to(dev).requires_grad_(v.dtype.is_floating_point and "empty_weight" not in k) for k, v in sd0.items()}
+        self.params = [v for v in self.sd.values() if v.requires_grad]
+        self.opt = torch.optim.Adam([{"params": [v for k, v in self.sd.items() if v.requires_grad and "vis_enc" in k], "lr": LR_ENC},
+                                     {"params": [v for k, v in self.sd.items() if v.requires_grad and "vis_enc" not in k], "lr": LR}],
+                                    betas=(0.9, 0.98), eps=1e-9, weight_decay=0, amsgrad=True)
+        self.om = cls(self.sd, "base", S, P, cfg["head"])
+        self.om.cfg["layers"] = layers
+        self.sched = torch.optim.lr_scheduler.MultiStepLR(self.opt, milestones=[int(0.7 * steps)], gamma=0.1)
+        self.seconds = 0.0
+        self.curve = []
+
+    def step(self, b):
+        t0 = time.perf_counter()
+        out = self.om.forward_train(b["img"], b["ref_expr_inds"], copy.deepcopy(b["img_metas"]), b["text_attention_mask"], b["gt_bbox"])
+        self.opt.zero_grad()
+        out[0]["loss_total"].backward()
+        torch.nn.utils.clip_grad_norm_(self.params, CLIP)
+        self.opt.step()
+        self.sched.step()
+        self.curve.append(float(out[0]["loss_total"].detach()))
+        torch.cuda.synchronize()
+        self.seconds += time.perf_counter() - t0
+
+    def predict(self, b):
+        return self.om.forward_test(b["img"], b["ref_expr_inds"], copy.deepcopy(b["img_metas"]), b["text_attention_mask"])[0]
+
+
+def run(steps=1500, B=32, S=128, layers=2, P=16, n_eval=8, log_every=100, out_path="gpurun_out/acc_parity.json", emulated=True):
+    """Arms: `product` (sm_100a kernels), `oracle` (fp32 reference arithmetic), and — to attribute whatever separates those two —
+    `oracle_bf16`: the same oracle with the product's bf16 operand roundings emulated in fp32 (oracle/bf16_emulation.py)."""
     from oracle import simvg_oracle as O   # checker: this file lives under tests/ because only tests may use the oracle
+    from oracle import bf16_emulation as OE
     from simvg_b200.optim import FusedAdamAMSGrad
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
@@ -74,22 +109,15 @@ def run(steps=1500, B=32, S=128, layers=2, P=16, n_eval=8, log_every=100, out_pa
     # ---- CUDA product
     model = model.cuda().eval()
     opt = FusedAdamAMSGrad(model, lr=LR, lr_vis_enc=LR_ENC, betas=(0.9, 0.98), eps=1e-9, grad_norm_clip=CLIP)
-    # ---- oracle arm: reference arithmetic + torch Adam(amsgrad) with the reference's lr groups and clip
-    sd = {k: v.clone().to(dev).requires_grad_(v.dtype.is_floating_point and "empty_weight" not in k) for k, v in sd0.items()}
-    params = [v for v in sd.values() if v.requires_grad]
-    ref_opt = torch.optim.Adam([{"params": [v for k, v in sd.items() if v.requires_grad and "vis_enc" in k], "lr": LR_ENC},
-                                {"params": [v for k, v in sd.items() if v.requires_grad and "vis_enc" not in k], "lr": LR}],
-                               betas=(0.9, 0.98), eps=1e-9, weight_decay=0, amsgrad=True)
-    om = O.OracleModel(sd, "base", S, P, cfg["head"])
-    om.cfg["layers"] = layers
-    # the reference's step schedule (core/scheduler.py: LambdaLR-style decay built ON the optimiser) drives both arms: x0.1 for
-    # the last 30 % of the steps, so both end converged instead of wherever their (chaotically diverging) trajectories happen to be
-    milestones = [int(0.7 * steps)]
-    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=milestones, gamma=0.1)
-    ref_sched = torch.optim.lr_scheduler.MultiStepLR(ref_opt, milestones=milestones, gamma=0.1)
+    # the reference's step schedule (core/scheduler.py: decay built ON the optimiser) drives every arm: x0.1 for the last 30 % of
+    # the steps, so all end converged instead of wherever their (chaotically diverging) trajectories happen to be
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[int(0.7 * steps)], gamma=0.1)
+    arms = {"oracle": _RefArm(O.OracleModel, sd0, cfg, S, P, layers, steps, dev)}
+    if emulated:
+        arms["oracle_bf16"] = _RefArm(OE.OracleModelBF16, sd0, cfg, S, P, layers, steps, dev)
 
     curve = []
-    t_gpu = t_ref = 0.0
+    t_gpu = 0.0
     for it in range(steps):
         b = task_batch(B, S, seed=1000 + it, device=dev)
         torch.cuda.synchronize()
@@ -100,44 +128,42 @@ def run(steps=1500, B=32, S=128, layers=2, P=16, n_eval=8, log_every=100, out_pa
         losses["loss_total"].backward()
         opt.step()
         sched.step()
-        lg = float(losses["loss_total"].detach())
+        curve.append(float(losses["loss_total"].detach()))
         t_gpu += time.perf_counter() - t0
-        t0 = time.perf_counter()
-        ol, _, _ = om.forward_train(b["img"], b["ref_expr_inds"], copy.deepcopy(b["img_metas"]), b["text_attention_mask"], b["gt_bbox"])
-        ref_opt.zero_grad()
-        ol["loss_total"].backward()
-        torch.nn.utils.clip_grad_norm_(params, CLIP)
-        ref_opt.step()
-        ref_sched.step()
-        lc = float(ol["loss_total"].detach())
-        t_ref += time.perf_counter() - t0
-        curve.append((lg, lc))
+        for arm in arms.values():
+            arm.step(b)
         if it % log_every == 0 or it == steps - 1:
-            print("step %4d  loss product %.4f  oracle %.4f  rel %.2e" % (it, lg, lc, abs(lg - lc) / max(abs(lc), 1e-9)), flush=True)
+            print("step %4d  loss product %.4f  %s" % (it, curve[-1], "  ".join("%s %.4f" % (k, a.curve[-1]) for k, a in arms.items())),
+                  flush=True)
 
     # ---- held-out evaluation (fixed seeds never seen in training)
-    res = {"product": {"dec": [], "tok": []}, "oracle": {"dec": [], "tok": []}}
+    names = ["product"] + list(arms)
+    res = {n: {"dec": [], "tok": []} for n in names}
     box_diff = 0.0
     for j in range(n_eval):
         b = task_batch(B, S, seed=900000 + j, device=dev)
         with torch.no_grad():
-            pg = model(b["img"], b["ref_expr_inds"], b["img_metas"], return_loss=False, text_attention_mask=b["text_attention_mask"])
-        pc, _ = om.forward_test(b["img"], b["ref_expr_inds"], copy.deepcopy(b["img_metas"]), b["text_attention_mask"])
-        for name, k in (("dec", 0), ("tok", 1)):
-            res["product"][name].append(float(accuracy_at_05(pg[k]["pred_bboxes"], b["gt_bbox"])))
-            res["oracle"][name].append(float(accuracy_at_05(pc[k]["pred_bboxes"], b["gt_bbox"])))
-        box_diff = max(box_diff, float((pg[0]["pred_bboxes"] - pc[0]["pred_bboxes"]).abs().max()) / S)
+            preds = {"product": model(b["img"], b["ref_expr_inds"], b["img_metas"], return_loss=False,
+                                      text_attention_mask=b["text_attention_mask"])}
+            for k, arm in arms.items():
+                preds[k] = arm.predict(b)
+        for n in names:
+            for name, k in (("dec", 0), ("tok", 1)):
+                res[n][name].append(float(accuracy_at_05(preds[n][k]["pred_bboxes"], b["gt_bbox"])))
+        box_diff = max(box_diff, float((preds["product"][0]["pred_bboxes"] - preds["oracle"][0]["pred_bboxes"]).abs().max()) / S)
     mean = lambda v: sum(v) / len(v)  # noqa: E731
-    tail = curve[-50:]
+    curves = {"product": curve, **{k: a.curve for k, a in arms.items()}}
     out = {"steps": steps, "batch": B, "img_size": S, "patch": P, "encoder_layers": layers, "held_out_images": n_eval * B,
            "lr": LR, "lr_vis_enc": LR_ENC, "grad_norm_clip": CLIP,
-           "acc05_decoder": {"product": mean(res["product"]["dec"]), "oracle": mean(res["oracle"]["dec"])},
-           "acc05_token": {"product": mean(res["product"]["tok"]), "oracle": mean(res["oracle"]["tok"])},
-           "final_loss_mean50": {"product": mean([a for a, _ in tail]), "oracle": mean([c for _, c in tail])},
-           "first_loss": {"product": curve[0][0], "oracle": curve[0][1]},
-           "first_step_rel_loss_gap": abs(curve[0][0] - curve[0][1]) / abs(curve[0][1]),
+           "acc05_decoder": {n: mean(res[n]["dec"]) for n in names},
+           "acc05_token": {n: mean(res[n]["tok"]) for n in names},
+           "final_loss_mean50": {n: mean(curves[n][-50:]) for n in names},
+           "loss_before_lr_decay_mean50": {n: mean(curves[n][int(0.7 * steps) - 50:int(0.7 * steps)]) for n in names},
+           "first_loss": {n: curves[n][0] for n in names},
+           "first_step_rel_loss_gap": abs(curve[0] - curves["oracle"][0]) / abs(curves["oracle"][0]),
            "max_pred_box_gap_frac_of_image": box_diff,
-           "seconds": {"product_train": t_gpu, "oracle_train": t_ref}, "oracle_device": "cuda:0 eager fp32 (TF32 off)"}
+           "seconds": {"product_train": t_gpu, **{k + "_train": a.seconds for k, a in arms.items()}},
+           "oracle_device": "cuda:0 eager fp32 (TF32 off)"}
     os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
     with open(out_path, "w") as f:
         json.dump(out, f, indent=1)
