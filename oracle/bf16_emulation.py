@@ -101,7 +101,7 @@ def encoder_forward(sd, cfg, image, ids, pad_mask, prefix=""):
     Lt = x2.shape[1]
     kpm = None
     if pad_mask is not None:
-        kpm = torch.cat([torch.zeros(B, split, dtype=torch.bool), pad_mask.bool()], dim=1)
+        kpm = torch.cat([torch.zeros(B, split, dtype=torch.bool, device=image.device), pad_mask.bool()], dim=1)
     xa = x1 + sd[p + "encoder.embed_positions.A.weight"][2:2 + split]
     xb = x2 + sd[p + "encoder.embed_positions.B.weight"][2:2 + Lt]
     if pad_mask is not None:

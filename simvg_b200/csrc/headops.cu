@@ -430,7 +430,6 @@ __global__ void __launch_bounds__(128) attn_small_bwd_kernel(const AttnSmall p) 
 // anywhere: per-chunk partial sums are written out and reduced by the following launch, so forward and backward are
 // deterministic.
 constexpr int XE = 256, XH = 8, XK = 32;     // model width, heads, keys per tile
-constexpr int XTS = XE + 1;                  // padded smem row of a key tile
 
 // u[r,h,:] = alpha * W_h^T x_h,  c[r,h] = alpha * x_h . b_h       (forward: x = q, W = Wk, alpha = scale;  backward: x = dctx, W = Wv)
 __global__ void __launch_bounds__(256) xattn_absorb_kernel(const float* __restrict__ x, const float* __restrict__ W,
@@ -456,48 +455,85 @@ __global__ void __launch_bounds__(256) xattn_absorb_kernel(const float* __restri
 }
 
 // out[(b*nq+i)*H + h][n] = vec[b*nq+i, h, :] . mat[b, n, :] + add[b*nq+i, h]     (-inf at masked keys when kpm is given)
-// grid (key tiles, B); warp = head, lane = key of the tile; two queries per pass over the staged tile.
+// The memory rows are streamed straight into registers, no shared memory (a staged-tile version was bound by shared-memory
+// wavefronts: every head re-read the tile).  A warp owns 8 consecutive keys, two at a time with the next two in flight; lane l
+// owns channels [8l, 8l + 8) of the key rows and of the eight head vectors (64 registers).  The eight per-head partial sums of a
+// key are reduced across the warp together: 4 + 2 + 1 shuffles halve the number of live values while halving the lane groups,
+// two more finish — 9 shuffles instead of 40 — and leave lane l with the total of head l >> 2.
+constexpr int XDK = 8;      // keys per warp
+
+__device__ __forceinline__ float xattn_reduce8(float (&s)[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float t[4], w[2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float send = b4 ? s[j] : s[j + 4], keep = b4 ? s[j + 4] : s[j];
+    t[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float send = b3 ? t[j] : t[j + 2], keep = b3 ? t[j + 2] : t[j];
+    w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const float send = b2 ? w[0] : w[1], keep = b2 ? w[1] : w[0];
+  float v = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;                 // total of head (lane >> 2)
+}
+
 __global__ void __launch_bounds__(256) xattn_dot_kernel(const float* __restrict__ vec, const float* __restrict__ add,
                                                         const float* __restrict__ mat, const unsigned char* __restrict__ kpm,
                                                         float* __restrict__ out, int nq, int N) {
-  extern __shared__ __align__(16) float xsm[];
-  float* tile = xsm;                   // [XK][XTS]
-  float* vs = xsm + XK * XTS;          // [2][XH][XE]
-  const int b = blockIdx.y, n0 = blockIdx.x * XK;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int idx = threadIdx.x; idx < XK * (XE / 4); idx += 256) {
-    const int k = idx >> 6, e4 = idx & 63;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n0 + k < N) v = *reinterpret_cast<const float4*>(mat + ((long long)b * N + n0 + k) * XE + e4 * 4);
-    float* t = tile + k * XTS + e4 * 4;
-    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
-  }
-  const int n = n0 + lane;
-  const bool live = n < N;
-  const bool masked = live && kpm != nullptr && kpm[(long long)b * N + n] != 0;
-  const float* t = tile + lane * XTS;
-  for (int i0 = 0; i0 < nq; i0 += 2) {
-    const int nqi = min(2, nq - i0);
-    __syncthreads();                   // tile staged (first pass) / previous vectors consumed
-    const float4* src = reinterpret_cast<const float4*>(vec + (long long)(b * nq + i0) * XH * XE);
-    for (int idx = threadIdx.x; idx < 2 * XH * XE / 4; idx += 256)
-      reinterpret_cast<float4*>(vs)[idx] = idx < nqi * XH * XE / 4 ? src[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const float* v0 = vs + warp * XE;
-    const float* v1 = vs + XH * XE + warp * XE;
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
-    for (int e = 0; e < XE; e += 4) {
-      const float4 x0 = *reinterpret_cast<const float4*>(v0 + e);
-      const float4 x1 = *reinterpret_cast<const float4*>(v1 + e);
-      const float t0 = t[e], t1 = t[e + 1], t2 = t[e + 2], t3 = t[e + 3];
-      a0 = fmaf(x0.x, t0, a0); a0 = fmaf(x0.y, t1, a0); a0 = fmaf(x0.z, t2, a0); a0 = fmaf(x0.w, t3, a0);
-      a1 = fmaf(x1.x, t0, a1); a1 = fmaf(x1.y, t1, a1); a1 = fmaf(x1.z, t2, a1); a1 = fmaf(x1.w, t3, a1);
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nbeg = (blockIdx.x * 8 + warp) * XDK;
+  if (nbeg >= N) return;
+  const int nend = min(nbeg + XDK, N);
+  const int head = lane >> 2, sub = lane & 3;
+  const float* mrow = mat + (long long)b * N * XE + lane * 8;
+  for (int i = 0; i < nq; ++i) {
+    const long long row0 = (long long)(b * nq + i) * XH;
+    float4 ua[XH], ub[XH];
+#pragma unroll
+    for (int h = 0; h < XH; ++h) {
+      const float* up = vec + (row0 + h) * XE + lane * 8;
+      ua[h] = *reinterpret_cast<const float4*>(up);
+      ub[h] = *reinterpret_cast<const float4*>(up + 4);
     }
-    if (live) {
-      const long long row0 = (long long)(b * nq + i0) * XH + warp;
-      out[row0 * N + n] = masked ? -INFINITY : a0 + add[row0];
-      if (nqi > 1) out[(row0 + XH) * N + n] = masked ? -INFINITY : a1 + add[row0 + XH];
+    const float addv = add[row0 + head];
+    float4 ka[2], kb[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const bool live = nbeg + t < nend;
+      ka[t] = live ? *reinterpret_cast<const float4*>(mrow + (long long)(nbeg + t) * XE) : make_float4(0.f, 0.f, 0.f, 0.f);
+      kb[t] = live ? *reinterpret_cast<const float4*>(mrow + (long long)(nbeg + t) * XE + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int n = nbeg; n < nend; n += 2) {
+      float4 na[2], nb[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {                 // the next two keys, in flight under this pair's FMAs and shuffles
+        const bool live = n + 2 + t < nend;
+        na[t] = live ? *reinterpret_cast<const float4*>(mrow + (long long)(n + 2 + t) * XE) : make_float4(0.f, 0.f, 0.f, 0.f);
+        nb[t] = live ? *reinterpret_cast<const float4*>(mrow + (long long)(n + 2 + t) * XE + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const bool mine = sub < 2 && n + sub < nend;
+      const bool masked = mine && kpm != nullptr && kpm[(long long)b * N + n + sub] != 0;
+      float v2[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float s[XH];
+#pragma unroll
+        for (int h = 0; h < XH; ++h) {
+          float a = ua[h].x * ka[t].x;
+          a = fmaf(ua[h].y, ka[t].y, a); a = fmaf(ua[h].z, ka[t].z, a); a = fmaf(ua[h].w, ka[t].w, a);
+          a = fmaf(ub[h].x, kb[t].x, a); a = fmaf(ub[h].y, kb[t].y, a); a = fmaf(ub[h].z, kb[t].z, a); a = fmaf(ub[h].w, kb[t].w, a);
+          s[h] = a;
+        }
+        v2[t] = xattn_reduce8(s, lane);
+      }
+      if (mine) out[(row0 + head) * N + n + sub] = masked ? -INFINITY : (sub == 0 ? v2[0] : v2[1]) + addv;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) { ka[t] = na[t]; kb[t] = nb[t]; }
     }
   }
 }
@@ -558,49 +594,67 @@ __global__ void __launch_bounds__(128) xattn_softmax_bwd_kernel(float* __restric
 
 // part[c][row, h, :] = sum_{n in key chunk c} w[row, h, n] * mat[b, n, :],   w = Wt * dropmask (drop_u may be null)
 // grid (chunks, B), thread = channel; four queries (32 weight rows) per pass over the chunk.
+template <int QG>      // queries per pass over the chunk: 1 when nq == 1 (8 accumulators: two CTAs per SM), else 4
 __global__ void __launch_bounds__(256) xattn_wsum_kernel(const float* __restrict__ Wt, const float* __restrict__ drop_u,
                                                          const float* __restrict__ mat, float* __restrict__ part, int nq, int N,
                                                          int CL, float drop_p) {
-  __shared__ __align__(16) float wsm[4 * XH][XK];
+  __shared__ __align__(16) float wsm[QG * XH][XK];
   const int b = blockIdx.y, c = blockIdx.x, e = threadIdx.x;
   const int nlo = c * CL, nhi = min(N, nlo + CL);
   const long long R = (long long)gridDim.y * nq;
-  for (int i0 = 0; i0 < nq; i0 += 4) {
-    const int rows = min(4, nq - i0) * XH;
-    float acc[4 * XH];
+  const bool drop = drop_u != nullptr && drop_p > 0.f;
+  const float keep = drop ? 1.f / (1.f - drop_p) : 1.f;
+  for (int i0 = 0; i0 < nq; i0 += QG) {
+    const int rows = min(QG, nq - i0) * XH;
+    float acc[QG * XH];
 #pragma unroll
-    for (int ih = 0; ih < 4 * XH; ++ih) acc[ih] = 0.f;
-    for (int n0 = nlo; n0 < nhi; n0 += XK) {
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < rows * XK; idx += 256) {
-        const int ih = idx >> 5, n = n0 + (idx & 31);
-        float w = 0.f;
-        if (n < nhi) {
-          const long long off = ((long long)(b * nq + i0) * XH + ih) * N + n;
-          w = Wt[off] * drop_scale(drop_u, off, drop_p);
-        }
-        wsm[ih][idx & 31] = w;
-      }
-      float v[XK];
+    for (int ih = 0; ih < QG * XH; ++ih) acc[ih] = 0.f;
+    // software pipeline over the chunk's key tiles: tile t + 1's memory rows and weights are loaded (registers) under tile t's FMAs
+    float v[XK], wr[QG], ur[QG];
+    auto fetch = [&](int n0) {
 #pragma unroll
       for (int k = 0; k < XK; ++k) v[k] = (n0 + k < nhi) ? mat[((long long)b * N + n0 + k) * XE + e] : 0.f;
-      __syncthreads();
 #pragma unroll
-      for (int ih = 0; ih < 4 * XH; ++ih) {
+      for (int q = 0; q < QG; ++q) {
+        const int idx = threadIdx.x + 256 * q, ih = idx >> 5, n = n0 + (idx & 31);
+        wr[q] = 0.f;
+        ur[q] = 1.f;
+        if (ih < rows && n < nhi) {
+          const long long off = ((long long)(b * nq + i0) * XH + ih) * N + n;
+          wr[q] = Wt[off];
+          if (drop) ur[q] = drop_u[off];
+        }
+      }
+    };
+    if (nlo < nhi) fetch(nlo);
+    for (int n0 = nlo; n0 < nhi; n0 += XK) {
+      __syncthreads();                                   // the previous tile's weights are consumed
+#pragma unroll
+      for (int q = 0; q < QG; ++q) {
+        const int idx = threadIdx.x + 256 * q;
+        if ((idx >> 5) < rows) wsm[idx >> 5][idx & 31] = wr[q] * ((!drop || ur[q] >= drop_p) ? keep : 0.f);
+      }
+      float vc[XK];
+#pragma unroll
+      for (int k = 0; k < XK; ++k) vc[k] = v[k];
+      __syncthreads();
+      if (n0 + XK < nhi) fetch(n0 + XK);
+#pragma unroll
+      for (int ih = 0; ih < QG * XH; ++ih) {
         if (ih < rows) {
 #pragma unroll
           for (int k = 0; k < XK; k += 4) {
             const float4 w4 = *reinterpret_cast<const float4*>(&wsm[ih][k]);
-            acc[ih] = fmaf(w4.x, v[k], acc[ih]);
-            acc[ih] = fmaf(w4.y, v[k + 1], acc[ih]);
-            acc[ih] = fmaf(w4.z, v[k + 2], acc[ih]);
-            acc[ih] = fmaf(w4.w, v[k + 3], acc[ih]);
+            acc[ih] = fmaf(w4.x, vc[k], acc[ih]);
+            acc[ih] = fmaf(w4.y, vc[k + 1], acc[ih]);
+            acc[ih] = fmaf(w4.z, vc[k + 2], acc[ih]);
+            acc[ih] = fmaf(w4.w, vc[k + 3], acc[ih]);
           }
         }
       }
     }
 #pragma unroll
-    for (int ih = 0; ih < 4 * XH; ++ih)
+    for (int ih = 0; ih < QG * XH; ++ih)
       if (ih < rows) part[(((long long)c * R + b * nq + i0) * XH + ih) * XE + e] = acc[ih];
   }
 }
@@ -650,44 +704,59 @@ __global__ void __launch_bounds__(256) xattn_bwd_kv_kernel(const float* __restri
   float* ds_s = xsm;                   // [IH][XK]
   float* pd_s = xsm + IH * XK;         // [IH][XK]
   const int b = blockIdx.y, n0 = blockIdx.x * XK, e = threadIdx.x;
+  // The accumulators START as the current gradients: the 64 read-modify-write loads of a thread are issued first and are in
+  // flight under the staging below (as `x[off] += acc` after the loop they were 64 serialised L2 round trips: 380 us / launch).
+  float ok[XK], ov[XK];
+#pragma unroll
+  for (int k = 0; k < XK; ++k) {
+    const bool live = n0 + k < N;
+    const long long off = ((long long)b * N + n0 + k) * XE + e;
+    ok[k] = live ? dkin[off] : 0.f;
+    ov[k] = live ? dval[off] : 0.f;
+  }
   for (int idx = threadIdx.x; idx < IH * XK; idx += 256) {
     const int ih = idx >> 5, n = n0 + (idx & 31);
-    float a = 0.f, w = 0.f;
+    float a = 0.f, w = 0.f, m = 1.f;
     if (n < N) {
       const long long off = ((long long)b * IH + ih) * N + n;
       a = ds[off];
-      w = P[off] * drop_scale(drop_u, off, drop_p);
+      w = P[off];
+      if (drop_u != nullptr && drop_p > 0.f) m = drop_u[off] >= drop_p ? 1.f / (1.f - drop_p) : 0.f;
     }
     ds_s[idx] = a;
-    pd_s[idx] = w;
+    pd_s[idx] = w * m;
   }
   __syncthreads();
-  float ok[XK], ov[XK];
+  for (int ih0 = 0; ih0 < IH; ih0 += 8) {        // eight rows' operands per L2 round trip
+    float uu[8], zz[8];
 #pragma unroll
-  for (int k = 0; k < XK; ++k) { ok[k] = 0.f; ov[k] = 0.f; }
-  float un = u[(long long)b * IH * XE + e], zn = dz[(long long)b * IH * XE + e];
-  for (int ih = 0; ih < IH; ++ih) {
-    const float uu = un, zz = zn;
-    if (ih + 1 < IH) {                 // next row's operands in flight under this row's FMAs
-      un = u[((long long)b * IH + ih + 1) * XE + e];
-      zn = dz[((long long)b * IH + ih + 1) * XE + e];
+    for (int j = 0; j < 8; ++j) {
+      const bool live = ih0 + j < IH;
+      uu[j] = live ? u[((long long)b * IH + ih0 + j) * XE + e] : 0.f;
+      zz[j] = live ? dz[((long long)b * IH + ih0 + j) * XE + e] : 0.f;
     }
 #pragma unroll
-    for (int k = 0; k < XK; k += 4) {
-      const float4 a4 = *reinterpret_cast<const float4*>(ds_s + ih * XK + k);
-      const float4 w4 = *reinterpret_cast<const float4*>(pd_s + ih * XK + k);
-      ok[k] = fmaf(a4.x, uu, ok[k]); ok[k + 1] = fmaf(a4.y, uu, ok[k + 1]);
-      ok[k + 2] = fmaf(a4.z, uu, ok[k + 2]); ok[k + 3] = fmaf(a4.w, uu, ok[k + 3]);
-      ov[k] = fmaf(w4.x, zz, ov[k]); ov[k + 1] = fmaf(w4.y, zz, ov[k + 1]);
-      ov[k + 2] = fmaf(w4.z, zz, ov[k + 2]); ov[k + 3] = fmaf(w4.w, zz, ov[k + 3]);
+    for (int j = 0; j < 8; ++j) {
+      if (ih0 + j < IH) {
+        const int ih = ih0 + j;
+#pragma unroll
+        for (int k = 0; k < XK; k += 4) {
+          const float4 a4 = *reinterpret_cast<const float4*>(ds_s + ih * XK + k);
+          const float4 w4 = *reinterpret_cast<const float4*>(pd_s + ih * XK + k);
+          ok[k] = fmaf(a4.x, uu[j], ok[k]); ok[k + 1] = fmaf(a4.y, uu[j], ok[k + 1]);
+          ok[k + 2] = fmaf(a4.z, uu[j], ok[k + 2]); ok[k + 3] = fmaf(a4.w, uu[j], ok[k + 3]);
+          ov[k] = fmaf(w4.x, zz[j], ov[k]); ov[k + 1] = fmaf(w4.y, zz[j], ov[k + 1]);
+          ov[k + 2] = fmaf(w4.z, zz[j], ov[k + 2]); ov[k + 3] = fmaf(w4.w, zz[j], ov[k + 3]);
+        }
+      }
     }
   }
 #pragma unroll
   for (int k = 0; k < XK; ++k) {
     if (n0 + k < N) {
       const long long off = ((long long)b * N + n0 + k) * XE + e;
-      dkin[off] += ok[k];
-      dval[off] += ov[k];
+      dkin[off] = ok[k];
+      dval[off] = ov[k];
     }
   }
 }
@@ -733,7 +802,7 @@ struct XPlan { int NC, CL; long long fwd_floats, bwd_floats; };
 static XPlan xattn_plan(int B, int nq, int N) {
   XPlan pl;
   const int tiles = (N + XK - 1) / XK;
-  pl.NC = tiles < 8 ? tiles : 8;
+  pl.NC = tiles < 16 ? tiles : 16;
   pl.CL = ((tiles + pl.NC - 1) / pl.NC) * XK;
   const long long R = (long long)B * nq, RHE = R * XH * XE, RH = R * XH;
   pl.fwd_floats = RHE + RH + pl.NC * RHE;
@@ -846,17 +915,17 @@ extern "C" int simvgb_head_xattn(const simvgb_head_xattn_args* a, int backward, 
   const int B = a->B, nq = a->nq, N = a->N, R = B * nq;
   const long long RHE = (long long)R * XH * XE, RH = (long long)R * XH;
   const dim3 tiles((N + XK - 1) / XK, B), chunks(pl.NC, B);
-  const int dot_smem = (XK * XTS + 2 * XH * XE) * (int)sizeof(float);
-  SIMVGB_CHECK(ensure_dynamic_smem((const void*)xattn_dot_kernel, dot_smem) == 0, "simvgb_head_xattn: shared memory opt-in failed");
+  const dim3 dotgrid((N + 8 * XDK - 1) / (8 * XDK), B);
   cudaStream_t st = S(stream);
   float* w = a->ws;
   if (!backward) {
     SIMVGB_CHECK(a->ctx && a->P && a->z && a->psum, "simvgb_head_xattn: forward needs ctx, P, z, psum");
     float *u = w, *c = u + RHE, *part = c + RH;
     xattn_absorb_kernel<<<R, 256, 0, st>>>(a->q, a->Wk, a->bk, u, c, a->scale);
-    xattn_dot_kernel<<<tiles, 256, dot_smem, st>>>(u, c, a->kin, a->kpm, a->P, nq, N);
+    xattn_dot_kernel<<<dotgrid, 256, 0, st>>>(u, c, a->kin, a->kpm, a->P, nq, N);
     xattn_softmax_kernel<<<(int)((RH + 3) / 4), 128, 0, st>>>(a->P, a->drop_u, a->psum, (int)RH, N, a->drop_p);
-    xattn_wsum_kernel<<<chunks, 256, 0, st>>>(a->P, a->drop_u, a->val, part, nq, N, pl.CL, a->drop_p);
+    if (nq == 1) xattn_wsum_kernel<1><<<chunks, 256, 0, st>>>(a->P, a->drop_u, a->val, part, nq, N, pl.CL, a->drop_p);
+    else xattn_wsum_kernel<4><<<chunks, 256, 0, st>>>(a->P, a->drop_u, a->val, part, nq, N, pl.CL, a->drop_p);
     xattn_out_kernel<<<R, 256, 0, st>>>(part, pl.NC, a->psum, a->Wv, a->bv, a->z, a->ctx, 1.f, 0, R);
   } else {
     SIMVGB_CHECK(a->dctx && a->P && a->z && a->psum && a->dq && a->dkin && a->dval && a->dWk && a->dbk && a->dWv && a->dbv,
@@ -868,9 +937,10 @@ extern "C" int simvgb_head_xattn(const simvgb_head_xattn_args* a, int backward, 
                  "simvgb_head_xattn: shared memory opt-in failed");
     xattn_absorb_kernel<<<R, 256, 0, st>>>(a->q, a->Wk, a->bk, u, c, a->scale);
     xattn_absorb_kernel<<<R, 256, 0, st>>>(a->dctx, a->Wv, a->bv, dz, dps, 1.f);
-    xattn_dot_kernel<<<tiles, 256, dot_smem, st>>>(dz, dps, a->val, nullptr, dP, nq, N);
+    xattn_dot_kernel<<<dotgrid, 256, 0, st>>>(dz, dps, a->val, nullptr, dP, nq, N);
     xattn_softmax_bwd_kernel<<<(int)((RH + 3) / 4), 128, 0, st>>>(dP, a->P, a->drop_u, dc, (int)RH, N, a->drop_p);
-    xattn_wsum_kernel<<<chunks, 256, 0, st>>>(dP, nullptr, a->kin, part, nq, N, pl.CL, 0.f);
+    if (nq == 1) xattn_wsum_kernel<1><<<chunks, 256, 0, st>>>(dP, nullptr, a->kin, part, nq, N, pl.CL, 0.f);
+    else xattn_wsum_kernel<4><<<chunks, 256, 0, st>>>(dP, nullptr, a->kin, part, nq, N, pl.CL, 0.f);
     xattn_bwd_kv_kernel<<<tiles, 256, kv_smem, st>>>(dP, a->P, a->drop_u, u, dz, a->dkin, a->dval, nq, N, a->drop_p);
     xattn_out_kernel<<<R, 256, 0, st>>>(part, pl.NC, dc, a->Wk, a->bk, du, a->dq, a->scale, 1, R);
     xattn_bwd_w_kernel<<<dim3(XE / 32, XH), 256, 0, st>>>(a->q, du, dc, a->dWk, a->dbk, a->scale, R);

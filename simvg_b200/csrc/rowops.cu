@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ln_bwd_kernel(const LnBwdParams p)
         for (int i = 0; i < 8; ++i) dr[i] += dx[i];
         store8(p.dres_out + row * C + col, dr);
         if (p.dyb != nullptr || p.dbias_prev != nullptr) {
-          const float sc = p.row_scale != nullptr ? __ldg(p.row_scale + row / p.rows_per_scale) : 1.0f;
+          const float sc = p.row_scale != nullptr ? __ldg(p.row_scale + (unsigned)row / (unsigned)p.rows_per_scale) : 1.0f;
 #pragma unroll
           for (int i = 0; i < 8; ++i) { dr[i] *= sc; acc_p[i] += dr[i]; }
           if (p.dyb != nullptr) store8(p.dyb + row * C + col, dr);
@@ -411,7 +411,12 @@ __global__ void __launch_bounds__(128) ln_bwd_warp_kernel(const LnBwdParams p) {
       }
     }
     const float c1 = warp_sum(s1) * (1.0f / C), c2 = warp_sum(s2) * (1.0f / C);
-    const float sc = (want_p && p.row_scale != nullptr) ? __ldg(p.row_scale + row / p.rows_per_scale) : 1.0f;
+    const float sc = (want_p && p.row_scale != nullptr) ? __ldg(p.row_scale + (unsigned)row / (unsigned)p.rows_per_scale) : 1.0f;
+    long long delta_base = 0;
+    if (MODE == 1 && p.delta != nullptr) {      // one 32-bit division per row (rows < 2^31), not a 64-bit one per chunk
+      const unsigned r32 = (unsigned)row, bb = r32 / (unsigned)p.delta_L, l = r32 - bb * (unsigned)p.delta_L;
+      delta_base = (long long)bb * p.delta_H * p.delta_stride + p.delta_vbase + l;
+    }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const long long off = row * C + (c * 32 + lane) * 8;
@@ -438,11 +443,7 @@ __global__ void __launch_bounds__(128) ln_bwd_warp_kernel(const LnBwdParams p) {
           d += __shfl_xor_sync(0xffffffffu, d, 1);
           d += __shfl_xor_sync(0xffffffffu, d, 2);
           d += __shfl_xor_sync(0xffffffffu, d, 4);
-          if ((lane & 7) == 0) {
-            const long long bb = row / p.delta_L;
-            const int l = (int)(row - bb * p.delta_L);
-            p.delta[(bb * p.delta_H + (c * 4 + (lane >> 3))) * p.delta_stride + p.delta_vbase + l] = d;
-          }
+          if ((lane & 7) == 0) p.delta[delta_base + (long long)(c * 4 + (lane >> 3)) * p.delta_stride] = d;
         }
       }
     }
