@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 INPUT_KINDS = {"img_u8": "uint8 HWC image (pre-Normalize); normalise + transpose fused into the patch-embed prologue on the GPU",
                "img": "float32 NCHW image, normalised on the host (the reference's collated input)"}
-TRAFFIC_ATTN_CFG2 = None   # filled from the round-2 ncu capture (profiles/r02_attention_ncu.md)
+TRAFFIC_ATTN_CFG2 = (797.8e6 + 167.1e6 + 966.7e6 + 594.6e6) / 2   # DRAM read + write of one fwd and one bwd launch (profiles/r02_kernels_ncu.md)
 
 CONFIGS = {
     #        vit      img  patch  bs  dec_layers branch_loss_weight
@@ -444,7 +444,7 @@ def run_ours(args, cfg_name):
         if cfg_name == "cfg2" and fam == "gemm":
             traffic, note = 597.5e6, "bytes/launch of the largest launch (QKV fwd GEMM, both experts), ncu capture in profiles/r01_gemm_ncu.md; algorithmic 644.5e6"
         elif cfg_name == "cfg2" and fam == "attention":
-            traffic, note = TRAFFIC_ATTN_CFG2, "mean DRAM bytes/launch over the family (fwd + bwd incl. delta / dq-convert), ncu captures in profiles/r02_attention_ncu.md"
+            traffic, note = TRAFFIC_ATTN_CFG2, "mean DRAM bytes/launch over the family (one forward + one backward launch per layer), ncu --set full captures in profiles/r02_kernels_ncu.md; algorithmic 637e6 (fwd) / 1274e6 (bwd)"
         roofline = {"bound": "tensor", "kernel": fam, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                     "traffic": traffic, "traffic_note": note,
                     "launches": n, "avg_ms": tot_ms / n, "peak_source": peak_src,
