@@ -181,6 +181,10 @@ class DetrTransformerEncoder(nn.Module):
         super().__init__()
         self.embed_dim, self.num_layers = embed_dim, num_layers
 
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("DetrTransformerEncoder is never executed by SimVG (every config builds the transformer with "
+                                  "only_decoder=True, transformer.py:192-194); only its constructor is part of the surface")
+
 
 class DetrTransformer(nn.Module):
     def __init__(self, encoder=None, decoder=None, only_decoder=False):
