@@ -90,6 +90,9 @@ class GraphedTrainStep:
                 del losses
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        # the warm-up's activations sit in the caching allocator's default pool; the capture allocates the same amount again in its
+        # private pool (ViT-L at bs 64: 2 x 97 GB > 180 GB) — hand the cached blocks back first
+        torch.cuda.empty_cache()
         K.reset_launch_count()
         # a process group's watchdog thread may touch CUDA while we capture: police this thread's calls only
         mode = "thread_local" if self.ddp is not None else "global"
