@@ -368,8 +368,20 @@ class FlatDDP:
         table.index_put_((all_ids,), all_rows * (1.0 / self.world), accumulate=True)
 
     # ---- hooks called by the encoder backward (simvg_b200/models/vis_encs/beit/beit3.py), overlap mode only
+    def _attach_foreign(self):
+        """If the trainer cleared gradients with model.zero_grad() / zero_grad(set_to_none=True), autograd allocated fresh p.grad
+        tensors for the non-encoder parameters: copy them into the flat buffers before those are exchanged (the encoder writes
+        its flat buffer directly)."""
+        if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+            return
+        for s in self.opt.segments:
+            if s is not self._enc_seg:
+                s.fb.ensure()
+                s.fb.attach_grads()
+
     def on_encoder_backward_start(self):
         """Head gradients are final once autograd reaches the encoder node."""
+        self._attach_foreign()
         for s in self.opt.segments:
             if s is not self._enc_seg:
                 self._reduce(s.fb.grad)
@@ -381,6 +393,7 @@ class FlatDDP:
         """Deferred mode: every gradient exchange of the step, issued after backward (between the two step graphs)."""
         if self.world <= 1:
             return
+        self._attach_foreign()
         for s in self.opt.segments:
             if s is self._enc_seg:
                 self._reduce_range(0, s.fb.numel, async_op=False)
@@ -419,6 +432,7 @@ class FlatDDP:
         if self.deferred:
             return self.exchange()
         if self._enc_seg is None or not self._work:
+            self._attach_foreign()
             for s in self.opt.segments:
                 if s is self._enc_seg:
                     self._reduce_range(0, s.fb.numel)

@@ -51,8 +51,18 @@ def _worker(rank, world, port, out):
     model(x).backward()
     local = opt.segments[0].fb.grad.clone()
     ddp.finish()
-    torch.save({"local": local, "avg": opt.segments[0].fb.grad.clone(), "w": model.a.weight.detach().clone()},
-               os.path.join(out, "r%d.pt" % rank))
+    res = {"local": local, "avg": opt.segments[0].fb.grad.clone(), "w": model.a.weight.detach().clone()}
+    # a trainer that clears gradients with model.zero_grad(set_to_none=True): autograd then allocates fresh p.grad tensors that
+    # no longer alias the flat buffer; the exchange must pick them up (and re-establish the aliasing), not reduce stale zeros
+    model.zero_grad(set_to_none=True)
+    opt.segments[0].fb.grad.zero_()
+    model(x).backward()
+    assert model.a.weight.grad.data_ptr() != opt.segments[0].fb.view(0, opt.segments[0].fb.grad).data_ptr()
+    ddp.finish()
+    res["avg_foreign"] = opt.segments[0].fb.grad.clone()
+    res["realiased"] = all(p.grad is None or p.grad.data_ptr() == opt.segments[0].fb.view(i, opt.segments[0].fb.grad).data_ptr()
+                           for i, p in enumerate(opt.segments[0].fb.params))
+    torch.save(res, os.path.join(out, "r%d.pt" % rank))
     dist.destroy_process_group()
 
 
@@ -153,6 +163,8 @@ def test_flat_ddp_world2_gloo(tmp_path):
     want = (r0["local"] + r1["local"]) / 2
     assert torch.allclose(r0["avg"], want, atol=1e-7) and torch.equal(r0["avg"], r1["avg"])
     assert float(want.abs().sum()) > 0
+    assert torch.allclose(r0["avg_foreign"], want, atol=1e-7) and torch.equal(r0["avg_foreign"], r1["avg_foreign"])
+    assert r0["realiased"] and r1["realiased"]
 
 
 def _crit_worker(rank, world, port, out):
