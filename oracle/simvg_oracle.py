@@ -452,6 +452,24 @@ def get_predictions(output, img_metas):
     return dict(pred_bboxes=torch.cat(boxes, 0), pred_masks=None, predict_classes=torch.cat(classes, 0))
 
 
+def get_predictions_grec(output, img_metas, rescale=False):
+    """MIXDETRMB.get_predictions_grec (mix_detr_mb.py:161-190): every non-empty box of every image, per-image dicts."""
+    if output["pred_logits"] is None:
+        return dict(pred_bboxes=None, pred_masks=None, predict_classes=None)
+    scores, labels = F.softmax(output["pred_logits"], dim=-1)[:, :, :-1].max(-1)
+    preds = []
+    for sc, lb, bp, meta in zip(scores, labels, output["pred_boxes"], img_metas):
+        h, w = meta["img_shape"][:2]
+        bx = box_cxcywh_to_xyxy(bp) * torch.as_tensor([w, h, w, h], dtype=bp.dtype, device=bp.device)
+        bx = torch.stack([bx[:, 0].clamp(0, w), bx[:, 1].clamp(0, h), bx[:, 2].clamp(0, w), bx[:, 3].clamp(0, h)], dim=-1)
+        keep = ((bx[:, 2] - bx[:, 0]) > 0) & ((bx[:, 3] - bx[:, 1]) > 0)
+        bx, sc, lb = bx[keep], sc[keep], lb[keep]
+        if rescale:
+            bx = bx / bx.new_tensor(meta["scale_factor"])
+        preds.append({"boxes": bx, "scores": sc, "labels": lb})
+    return dict(pred_bboxes=preds, pred_masks=None)
+
+
 # =============================================================================================== detector
 class OracleModel:
     """MIXDETRMB (det_seg/mix_detr_mb.py:13-125) over a reference-keyed state dict."""

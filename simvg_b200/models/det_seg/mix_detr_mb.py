@@ -10,7 +10,6 @@ import torch.nn.functional as F
 
 from simvg_b200.core.box_ops import box_cxcywh_to_xyxy, image_scale_tensor
 from simvg_b200.models.builder import MODELS
-from simvg_b200.structures import detector_postprocess
 
 from .one_stage import OneStageModel
 
@@ -84,17 +83,28 @@ class MIXDETRMB(OneStageModel):
         return dict(pred_bboxes=best, pred_masks=None, predict_classes=classes)
 
     def get_predictions_grec(self, output, img_metas, rescale=False):
-        """mix_detr_mb.py:161-190."""
+        """Every non-empty box of every image as per-image dicts (mix_detr_mb.py:161-190 + tgqs_kd_detr_head.py:577-604 +
+        detectron2 detector_postprocess).  Scores, scaling, clipping and the non-empty test are batched on the device; the
+        per-image dicts are views of the batch tensors, and the only host synchronisation is ONE `keep.all()` for the batch
+        (the reference: a filter + index per image) — when it holds, which it does unless a box degenerates, nothing is indexed."""
         box_cls, box_pred = output["pred_logits"], output["pred_boxes"]
         if box_cls is None:
             return dict(pred_bboxes=None, pred_masks=None, predict_classes=None)
-        sizes = [m["img_shape"] for m in img_metas]
-        results = self.head.inference(box_cls, box_pred, sizes)
+        B = box_cls.shape[0]
+        scores, labels = F.softmax(box_cls, dim=-1)[:, :, :-1].max(-1)
+        whwh = image_scale_tensor(img_metas, box_pred.device, box_pred.dtype, repeat=2).unsqueeze(1)   # [B, 1, (w, h, w, h)]
+        boxes = box_cxcywh_to_xyxy(box_pred) * whwh
+        boxes = torch.min(boxes.clamp(min=0), whwh)
+        keep = ((boxes[..., 2] - boxes[..., 0]) > 0) & ((boxes[..., 3] - boxes[..., 1]) > 0)
+        if rescale:
+            sf = torch.tensor([m["scale_factor"] for m in img_metas], dtype=boxes.dtype).to(boxes.device)
+            boxes = boxes / sf.unsqueeze(1)
+        all_kept = bool(keep.all())
         preds = []
-        for r, meta in zip(results, img_metas):
-            r = detector_postprocess(r, meta["img_shape"][0], meta["img_shape"][1])
-            box = r.pred_boxes.tensor
-            if rescale:
-                box = box / box.new_tensor(meta["scale_factor"])
-            preds.append({"boxes": box, "scores": r.scores, "labels": r.pred_classes})
+        for b in range(B):
+            if all_kept:
+                preds.append({"boxes": boxes[b], "scores": scores[b], "labels": labels[b]})
+            else:
+                k = keep[b]
+                preds.append({"boxes": boxes[b][k], "scores": scores[b][k], "labels": labels[b][k]})
         return dict(pred_bboxes=preds, pred_masks=None)

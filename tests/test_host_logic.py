@@ -431,3 +431,34 @@ def test_chunked_backward_plan_tiles_the_encoder_gradient_buffer():
         ranges.sort()
         assert ranges[0][0] == 0 and ranges[-1][1] == fb.numel
         assert all(a[1] == b[0] for a, b in zip(ranges[:-1], ranges[1:])), (cl, ranges)
+
+
+def test_grec_predictions_batched_equal_the_per_image_path():
+    """get_predictions_grec (all non-empty boxes per image, mix_detr_mb.py:161-190) batched on the device vs the oracle's
+    per-image restatement: images of different sizes, rescale on / off, and a batch containing degenerate (empty after clipping)
+    boxes, which must be dropped exactly where detectron2's `nonempty()` drops them."""
+    from oracle import simvg_oracle as O
+    from simvg_b200.models.det_seg.mix_detr_mb import MIXDETRMB
+    g = torch.Generator().manual_seed(3)
+    B, nq = 3, 10
+    metas = [{"img_shape": (64, 96, 3), "scale_factor": [1.5, 1.0, 1.5, 1.0]}, {"img_shape": (80, 80, 3), "scale_factor": [2.0, 2.0, 2.0, 2.0]},
+             {"img_shape": (50, 70, 3), "scale_factor": [0.5, 0.7, 0.5, 0.7]}]
+    logits = torch.randn(B, nq, 2, generator=g)
+    boxes = torch.rand(B, nq, 4, generator=g) * 0.5 + 0.2
+    model = MIXDETRMB.__new__(MIXDETRMB)       # the method only touches its arguments
+    for degenerate in (False, True):
+        bx = boxes.clone()
+        if degenerate:
+            bx[0, 3] = torch.tensor([1.4, 0.5, 0.2, 0.2])      # entirely right of the image: zero width after clipping
+            bx[2, 0] = torch.tensor([0.5, 0.5, 0.0, 0.3])      # zero width
+        out = {"pred_logits": logits, "pred_boxes": bx}
+        for rescale in (False, True):
+            got = MIXDETRMB.get_predictions_grec(model, out, metas, rescale=rescale)["pred_bboxes"]
+            want = O.get_predictions_grec(out, metas, rescale=rescale)["pred_bboxes"]
+            assert len(got) == len(want) == B
+            for a, b in zip(got, want):
+                assert a["boxes"].shape == b["boxes"].shape, (degenerate, a["boxes"].shape, b["boxes"].shape)
+                assert torch.allclose(a["boxes"], b["boxes"], atol=1e-5) and torch.equal(a["labels"], b["labels"])
+                assert torch.allclose(a["scores"], b["scores"])
+        if degenerate:
+            assert got[0]["boxes"].shape[0] == nq - 1 and got[2]["boxes"].shape[0] == nq - 1 and got[1]["boxes"].shape[0] == nq
