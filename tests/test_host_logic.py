@@ -462,3 +462,50 @@ def test_grec_predictions_batched_equal_the_per_image_path():
                 assert torch.allclose(a["scores"], b["scores"])
         if degenerate:
             assert got[0]["boxes"].shape[0] == nq - 1 and got[2]["boxes"].shape[0] == nq - 1 and got[1]["boxes"].shape[0] == nq
+
+
+def test_cabi_round2_entry_points_validate_without_gpu(lib):
+    """The entry points added in round 2 follow the same convention: argument errors return < 0 with a message before any
+    device call (so they can be exercised on a box without a GPU); the cross-attention scratch size is a pure function."""
+    from simvg_b200 import kernels as K
+    K._lib_setup()
+    # head linear / LayerNorm / attention: null pointers and unsupported shapes
+    a = K.HeadLinArgs()
+    assert lib.simvgb_head_lin_fwd(ctypes.byref(a), None) < 0 and b"null pointer" in lib.simvgb_last_error()
+    assert lib.simvgb_head_lin_bwd(ctypes.byref(a), None) < 0
+    ln = K.HeadLnArgs()
+    buf = (ctypes.c_float * 8)()
+    ln.a = ln.gamma = ctypes.cast(buf, ctypes.c_void_p)
+    ln.R, ln.C = 4, 384
+    assert lib.simvgb_head_lnres(ctypes.byref(ln), 0, None) < 0 and b"256 or 512" in lib.simvgb_last_error()
+    at = K.HeadAttnArgs()
+    at.q = at.k = at.v = ctypes.cast(buf, ctypes.c_void_p)
+    at.B, at.nq, at.nk, at.H = 1, 1, 33, 8
+    assert lib.simvgb_head_attn_small(ctypes.byref(at), 0, None) < 0 and b"nk <= 32" in lib.simvgb_last_error()
+    xa = K.HeadXAttnArgs()
+    for f in ("q", "kin", "val", "Wk", "bk", "Wv", "bv"):
+        setattr(xa, f, ctypes.cast(buf, ctypes.c_void_p))
+    xa.B, xa.nq, xa.N, xa.E, xa.H = 2, 1, 100, 128, 8
+    assert lib.simvgb_head_xattn(ctypes.byref(xa), 0, None) < 0 and b"E = 256" in lib.simvgb_last_error()
+    xa.E = 256
+    assert lib.simvgb_head_xattn(ctypes.byref(xa), 0, None) < 0 and b"workspace" in lib.simvgb_last_error()
+    # scratch: forward = u + c + NC partial sums; NC = min(16, key tiles of 32); backward adds dz, dps, dc, the score gradients, du
+    ws = lib.simvgb_head_xattn_ws_floats
+    R, N = 64, 1600
+    nc = min(16, (N + 31) // 32)
+    assert ws(64, 1, N, 0) == R * 2048 + R * 8 + nc * R * 2048
+    assert ws(64, 1, N, 1) == 2 * (R * 2048 + R * 8) + 2 * R * 8 + R * 8 * N + nc * R * 2048 + R * 2048 - R * 8
+    assert ws(2, 10, 40, 0) == 20 * 2048 + 20 * 8 + 2 * 20 * 2048
+    assert ws(0, 1, 10, 0) < 0
+    # Hungarian / uint8 patch gather
+    assert lib.simvgb_hungarian(None, 1, 1, 1, None, None, None, 1, None) < 0
+    i64 = (ctypes.c_int64 * 4)()
+    i32 = (ctypes.c_int32 * 4)()
+    assert lib.simvgb_hungarian(buf, 1, 33, 1, i32, i64, i64, 1, None) < 0 and b"bad shape" in lib.simvgb_last_error()
+    mean = (ctypes.c_float * 3)(1, 1, 1)
+    std0 = (ctypes.c_float * 3)(1, 0, 1)
+    assert lib.simvgb_im2col_patch_u8(buf, buf, 1, 64, 12, mean, mean, 1, None) < 0      # P % 8 != 0
+    assert lib.simvgb_im2col_patch_u8(buf, buf, 1, 64, 16, mean, std0, 1, None) < 0 and b"zero std" in lib.simvgb_last_error()
+    h, m = ctypes.c_longlong(-1), ctypes.c_longlong(-1)
+    lib.simvgb_tmap_cache_stats(ctypes.byref(h), ctypes.byref(m))
+    assert h.value >= 0 and m.value >= 0
