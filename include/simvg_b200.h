@@ -193,7 +193,8 @@ int simvgb_adam_amsgrad_dev(float* p, const float* g, float* m, float* v, float*
 typedef struct simvgb_head_lin_args {
   /* forward: y[r,n] = dropout(relu?( sum_k (x[r,k] + (n < n_split ? x2[r,k] : 0)) W[n,k] + b[n] ))
    * k_splits > 1: partial sums are atomically added into a ZEROED y (bias from split 0), no relu / dropout.
-   * backward: dx (+ dx2 for the columns < n_split) += dY_eff W,  dW += dY_eff^T x_in,  db += colsum(dY_eff); NULL = skip. */
+   * backward: dx (+ dx2 for the columns < n_split) += dY_eff W,  dW += dY_eff^T x_in,  db += colsum(dY_eff); NULL = skip.
+   * (nn.Linear forward / backward: heads/utils.py:7-46, the in / out projections of nn.MultiheadAttention and detrex FFN.) */
   const float* x;        /* [R, K] */
   const float* x2;       /* [R, K] or NULL (position embedding added to the input of the first n_split outputs) */
   const float* W;        /* [N, K] */
@@ -212,7 +213,7 @@ int simvgb_head_lin_fwd(const simvgb_head_lin_args* args, void* stream);
 int simvgb_head_lin_bwd(const simvgb_head_lin_args* args, void* stream);
 
 typedef struct simvgb_head_ln_args {
-  /* forward: s = a + dropout(b);  y = LayerNorm(s) * gamma + beta  (mean / rstd written).   C <= 512, multiple of 32.
+  /* forward: s = a + dropout(b);  y = LayerNorm(s) * gamma + beta  (mean / rstd written).   C = 256 or 512.
    * backward: ds = LN'(dy);  da += ds;  db += ds * dropmask;  dgamma += sum dy * xhat;  dbeta += sum dy. */
   const float* a;        /* [R, C] */
   const float* b;        /* [R, C] or NULL */
