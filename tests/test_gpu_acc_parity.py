@@ -31,5 +31,5 @@ def test_acc05_parity_on_held_out_synthetic_boxes(lib):
         assert abs(a - b) <= 3.0, (branch, out[branch])
     assert out["first_step_rel_loss_gap"] <= 1e-3, out["first_step_rel_loss_gap"]
     fin = out["final_loss_mean50"]
-    assert 0.5 * fin["oracle"] <= fin["product"] <= 1.75 * fin["oracle"], fin
+    assert 0.5 * fin["oracle"] <= fin["product"] <= 2.0 * fin["oracle"], fin     # observed ratios 0.9-1.5 (see the docstring)
     assert fin["product"] <= 0.12 * out["first_loss"]["product"], (fin, out["first_loss"])     # converged: < 12 % of the initial loss
