@@ -191,6 +191,35 @@ def golden_state_dict_keys():
     print("state-dict keys:", {k: len(v) for k, v in out.items()})
 
 
+def golden_grec_predictions():
+    """gREC post-processing (all non-empty boxes per image) by the reference's own MIXDETRMB.get_predictions_grec +
+    TextGuidedQuerySelectKDDETRHead.inference (mix_detr_mb.py:161-190, tgqs_kd_detr_head.py:577-604) over the detectron2 shims:
+    images of different sizes, rescale on / off, boxes that are empty after clipping."""
+    _, _, _, build_model = load_reference()
+    torch.manual_seed(6666)
+    ref = build_model(copy.deepcopy(model_cfg("base", 64, 32, num_decoder_layers=1, num_queries=10))).eval()
+    g = torch.Generator().manual_seed(3)
+    B, nq = 3, 10
+    metas = [{"img_shape": (64, 96, 3), "scale_factor": [1.5, 1.0, 1.5, 1.0]}, {"img_shape": (80, 80, 3), "scale_factor": [2.0, 2.0, 2.0, 2.0]},
+             {"img_shape": (50, 70, 3), "scale_factor": [0.5, 0.7, 0.5, 0.7]}]
+    logits = torch.randn(B, nq, 2, generator=g)
+    boxes = torch.rand(B, nq, 4, generator=g) * 0.5 + 0.2
+    boxes[0, 3] = torch.tensor([1.4, 0.5, 0.2, 0.2])      # entirely right of the image: zero width after clipping
+    boxes[2, 0] = torch.tensor([0.5, 0.5, 0.0, 0.3])      # zero width
+    fixture = {"logits": logits, "boxes": boxes, "metas": metas}
+    for rescale in (False, True):
+        with torch.no_grad():
+            got = ref.get_predictions_grec({"pred_logits": logits.clone(), "pred_boxes": boxes.clone()}, copy.deepcopy(metas),
+                                           rescale=rescale)["pred_bboxes"]
+        want = O.get_predictions_grec({"pred_logits": logits, "pred_boxes": boxes}, metas, rescale=rescale)["pred_bboxes"]
+        for a, b in zip(got, want):
+            assert a["boxes"].shape == b["boxes"].shape and torch.allclose(a["boxes"], b["boxes"], atol=1e-5)
+            assert torch.equal(a["labels"], b["labels"]) and torch.allclose(a["scores"], b["scores"])
+        fixture["rescale_%d" % int(rescale)] = [{k: v.detach().clone() for k, v in d.items()} for d in got]
+    print("grec predictions: boxes kept per image", [len(d["boxes"]) for d in fixture["rescale_0"]])
+    torch.save(fixture, os.path.join(OUT, "grec_predictions.pt"))
+
+
 def golden_known_answers():
     """Quirk known-answer vectors computed by the reference's own heads/utils.py."""
     import importlib
@@ -215,4 +244,5 @@ if __name__ == "__main__":
     golden_cfg1()
     golden_interpolate()
     golden_state_dict_keys()
+    golden_grec_predictions()
     print("golden fixtures written to", OUT)
