@@ -220,6 +220,44 @@ def golden_grec_predictions():
     torch.save(fixture, os.path.join(OUT, "grec_predictions.pt"))
 
 
+class _EmaToy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(6, 5)
+        self.b = torch.nn.LayerNorm(5)
+        self.register_buffer("running", torch.zeros(5))
+
+
+def golden_ema():
+    """ExponentialMovingAverage by the reference's own class (simvg/models/utils.py:130-180; the file only needs torch / numpy, so it
+    is loaded directly rather than through the shim package): five update_params() calls over seeded parameter / buffer changes,
+    then apply_shadow() / restore()."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_models_utils", "/root/reference/simvg/models/utils.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(17)
+    model = _EmaToy()
+    init = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ema = mod.ExponentialMovingAverage(model, 0.9)
+    for step in range(5):
+        g = torch.Generator().manual_seed(100 + step)
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(torch.randn(p.shape, generator=g) * 0.1)
+            model.running.add_(torch.randn(5, generator=g))
+        ema.update_params()
+    live = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    shadow = {k: v.detach().clone() for k, v in ema.shadow.items()}
+    ema.apply_shadow()
+    applied = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ema.restore()
+    assert all(torch.equal(model.state_dict()[k], live[k]) for k in live)
+    torch.save({"init": init, "steps": 5, "alpha": 0.9, "live": live, "shadow": shadow, "applied": applied, "ema_step": ema.step},
+               os.path.join(OUT, "ema.pt"))
+    print("ema: step", ema.step, "shadow a.weight[0,:3]", shadow["a.weight"][0, :3].tolist())
+
+
 def golden_known_answers():
     """Quirk known-answer vectors computed by the reference's own heads/utils.py."""
     import importlib
@@ -245,4 +283,5 @@ if __name__ == "__main__":
     golden_interpolate()
     golden_state_dict_keys()
     golden_grec_predictions()
+    golden_ema()
     print("golden fixtures written to", OUT)
