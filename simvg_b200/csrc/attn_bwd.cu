@@ -46,9 +46,6 @@ constexpr int kComputeThreads = 512;    // four warps per TMEM lane quarter, one
 #ifndef SIMVGB_BWD_POLY
 #define SIMVGB_BWD_POLY 0
 #endif
-#ifndef SIMVGB_BWD_DQ_PAIR
-#define SIMVGB_BWD_DQ_PAIR 1   // lane pairs exchange halves of their dQ rows so each red.v4 pair covers a 32-byte sector
-#endif
 #ifndef SIMVGB_BWD_STAGES
 #define SIMVGB_BWD_STAGES 3
 #endif
